@@ -1,0 +1,165 @@
+/*
+ * mpsnerf.h -- C ABI of libmpsnerf_b200.so: the B200 (sm_100a) implementation of
+ * MPS-NeRF's per-ray render hot path.
+ *
+ * The reference (gaoxiangjun/MPS-NeRF) is pure Python/PyTorch and has no FFI layer,
+ * so every entry point below replaces a *Python* function of the reference; the
+ * file:line it replaces is cited per function (paths relative to the reference root).
+ * The host-side mirror of the reference API (mpsnerf_b200.run_nerf_batch, .lib.*)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless named host_*; all floats are fp32, row major;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - no entry point allocates, synchronises the device or throws; each returns 0 on success
+ *    or a negative MPSNERF_E* code, with a message available from mpsnerf_last_error()
+ *    (thread-local);
+ *  - every entry point is re-entrant per stream: all state lives in caller-owned buffers.
+ */
+#ifndef MPSNERF_H_
+#define MPSNERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPSNERF_ABI_VERSION 1
+
+#define MPSNERF_OK 0
+#define MPSNERF_EINVAL (-1)   /* bad argument (null pointer, size out of range) */
+#define MPSNERF_ECUDA (-2)    /* a CUDA runtime call or launch failed */
+#define MPSNERF_EARCH (-3)    /* device is not sm_100 */
+
+#define MPSNERF_MAX_VIEWS 8
+#define MPSNERF_NUM_JOINTS 24
+#define MPSNERF_GRID_MAX_DIM 64
+#define MPSNERF_TOKEN_DIM 155       /* 128 latent + 27 rgb code (lib/skinnning_batch.py:161) */
+#define MPSNERF_TOKEN_LD 160        /* padded row stride used by the tensor-core path */
+
+/* Per-(source,target) frame constants, filled by the host once per render() call.
+ * A_* are the 24 LBS transforms as 3x4 row-major blocks (lib/run_nerf_helpers.py:227-254):
+ *   A_tp      target pose, target shape      (lib/skinnning_batch.py:206)
+ *   A_big_tp  "big pose", target shape       (lib/skinnning_batch.py:243)
+ *   A_big_sp  "big pose", source shape       (lib/skinnning_batch.py:266)
+ *   A_sp      source pose, source shape      (lib/skinnning_batch.py:289) */
+typedef struct mpsnerf_frame {
+  float Th_tp[3];
+  float R_tp[9];
+  float Rinv_sp[9];
+  float Th_sp[3];
+  float A_tp[MPSNERF_NUM_JOINTS * 12];
+  float A_big_tp[MPSNERF_NUM_JOINTS * 12];
+  float A_big_sp[MPSNERF_NUM_JOINTS * 12];
+  float A_sp[MPSNERF_NUM_JOINTS * 12];
+  float cam_R[MPSNERF_MAX_VIEWS * 9];   /* R_all  (lib/skinnning_batch.py:177-184) */
+  float cam_T[MPSNERF_MAX_VIEWS * 3];   /* T_all */
+  float cam_K[MPSNERF_MAX_VIEWS * 9];   /* K_all */
+  int32_t n_views;
+  int32_t img_w, img_h;                 /* size of img_all: image_shape = [W, H] (:186-189) */
+  int32_t feat_w, feat_h;               /* size of the encoder latent */
+  int32_t reserved[3];
+} mpsnerf_frame;
+
+const char* mpsnerf_last_error(void);
+int mpsnerf_abi_version(void);
+/* 0 if device `dev` can run this library (compute capability 10.x), else MPSNERF_EARCH. */
+int mpsnerf_check_device(int dev);
+
+/* ---- nearest-vertex acceleration grid -------------------------------------------------
+ * Replaces the brute-force pytorch3d knn_points calls (lib/skinnning_batch.py:214,256,357)
+ * with an exact uniform-grid search.  If Th/R are non-null the vertices are first taken to
+ * SMPL space, v' = (v - Th) @ R (lib/skinnning_batch.py:355-356), with pinned fp32 ops. */
+size_t mpsnerf_grid_bytes(int n_verts);
+int mpsnerf_grid_build(const float* verts, int n_verts, const float* Th, const float* R,
+                       float cell, void* grid, size_t grid_bytes, void* stream);
+
+/* Exact K=1 nearest vertex for arbitrary queries (diagnostic / mesh-extraction use;
+ * extract_thuman_mesh.py:132).  d2 = (dx*dx+dy*dy)+dz*dz, ties -> lowest index. */
+int mpsnerf_knn1(const float* query, int64_t n, const void* grid, float* d2_out,
+                 int32_t* idx_out, void* stream);
+
+/* ---- K1: stratified sampling + world->SMPL + human-region mask + argmin + compaction ---
+ * Replaces render_rays sampling (run_nerf_batch.py:406-424), run_network flattening
+ * (:42-52) and SKinningBatch.forward steps 2,4 (lib/skinnning_batch.py:345-365).
+ *   rays     (n_rays, 8): o(3) d(3) near far
+ *   t_vals   (S) = torch.linspace(0,1,S);  u (n_rays,S) uniforms or NULL (perturb == 0)
+ *   points   optional (n_rays*S,3): if non-null the sample points are READ from here
+ *            instead of being generated (network_fn called directly on points)
+ * Outputs for all P = n_rays*S points:
+ *   raw (P,4) = -80 where inactive (left untouched where active), pts_mask (P) 0/1,
+ *   smpl_query (P,3), smpl_src (P,3) zero-filled for inactive points;
+ * and the compacted active list (capacity P): act_pid, act_idx2, act_q (cap,3), *act_count.
+ * act_count must be zeroed by the caller before the first launch of a frame. */
+int mpsnerf_sample_knn(const float* rays, int64_t n_rays, int32_t S, const float* t_vals,
+                       const float* u, const float* points, const mpsnerf_frame* frame,
+                       const void* grid_tp, float* raw, float* pts_mask, float* smpl_query,
+                       float* smpl_src, int32_t* act_pid, int32_t* act_idx2, float* act_q,
+                       int32_t* act_count, void* stream);
+
+/* ---- K3: inverse LBS target->canonical->source + projection ---------------------------
+ * Replaces coarse_deform_target2c (lib/skinnning_batch.py:203-251), coarse_deform_c2source
+ * (:253-300) and projection (:177-184) for mean_shape = 0.
+ *   skin_w (n_verts,24) SMPL blend weights.  Works on active points [first, first+count).
+ * Outputs: xc (count,3) canonical points, uv (count,V,2) pixels, smpl_src[pid] scattered;
+ * optional idx3 / xw (count) for diagnostics (may be NULL).
+ * identity_canonical != 0 reproduces extract_mesh mode (:394-396): canonical = query point. */
+int mpsnerf_deform_project(const int32_t* act_pid, const int32_t* act_idx2, const float* act_q,
+                           int64_t first, int64_t count, const float* skin_w,
+                           const mpsnerf_frame* frame, const void* grid_tv, float* xc, float* uv,
+                           float* smpl_src, int32_t* idx3, float* xw, int identity_canonical,
+                           void* stream);
+
+/* ---- K4: multiview bilinear feature + RGB lookup, RGB positional code -> tokens --------
+ * Replaces SpatialEncoder.index / grid_sample (lib/encoder.py:12-62, 225-253) and the RGB
+ * append (lib/skinnning_batch.py:428-435).  latent is NHWC (V,Hf,Wf,128); img is NHWC with
+ * 4 floats per pixel (V,H,W,4: r,g,b,0).  tokens (count, V, ld) with ld >= 155; pad = 0. */
+int mpsnerf_gather_tokens(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
+                          const float* latent, const float* img4, float* tokens, int32_t ld,
+                          void* stream);
+
+/* ---- K5: cross-view transformer + canonical NeRF MLP -----------------------------------
+ * Replaces Transformer.forward (lib/transformer.py:74-86) and the MLP of
+ * SKinningBatch.forward (lib/skinnning_batch.py:438-473); scatters [rgb, alpha] to
+ * raw[act_pid[first + i]].
+ * fp32 variant: SIMT, plain torch-layout weights passed as an array of device pointers in
+ * the order documented in mpsnerf_b200/engine.py::DENSE_FP32_ORDER.  workspace >=
+ * mpsnerf_dense_fp32_workspace(count) bytes. */
+size_t mpsnerf_dense_fp32_workspace(int64_t count, int n_views);
+int mpsnerf_dense_fp32(const float* tokens, int32_t ld, const float* xc, int64_t count,
+                       int n_views, const float* const* weights, const int32_t* act_pid,
+                       int64_t first, float* raw, void* workspace, void* stream);
+
+/* bf16 tensor-core variant (tcgen05 / TMEM / bulk-async weight streaming).  `packed` is the
+ * blob produced by mpsnerf_b200.engine.pack_weights_bf16 (layout: DESIGN.md section 5). */
+size_t mpsnerf_dense_bf16_workspace(int64_t count, int n_views);
+int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* xc, int64_t count,
+                       int n_views, const void* packed, size_t packed_bytes,
+                       const int32_t* act_pid, int64_t first, float* raw, void* workspace,
+                       void* stream);
+
+/* ---- K6: alpha compositing --------------------------------------------------------------
+ * Replaces raw2outputs (run_nerf_batch.py:369-398).  One warp per ray.
+ *   raw (n_rays,S,4); z is regenerated from rays/t_vals/u exactly as in K1, or read from
+ *   z_vals (n_rays,S) when that is non-null (rays then only supplies the directions).
+ * Outputs rgb (n_rays,3), disp, acc, depth (n_rays; depth may be NULL); optional (NULL ok)
+ * weights and transmittance T_s, both (n_rays,S). */
+int mpsnerf_composite(const float* raw, const float* rays, int64_t n_rays, int32_t S,
+                      const float* t_vals, const float* u, const float* z_vals, int occupancy,
+                      float* rgb, float* disp, float* acc, float* depth, float* weights,
+                      float* trans, void* stream);
+
+/* Diagnostic: one 128 x N x K bf16 tcgen05 GEMM tile through the same shared-memory layout,
+ * descriptors and TMEM epilogue the fused kernels use.  a (128,K) row-major bf16 (as uint16);
+ * b_packed = the (N,K) weight in the SWIZZLE_128B chunk layout produced by
+ * mpsnerf_b200.engine.pack_kmajor_sw128; d (128,N) fp32.  K % 64 == 0, N % 16 == 0, N <= 256. */
+int mpsnerf_selftest_umma(const uint16_t* a, const uint8_t* b_packed, float* d, int N, int K,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPSNERF_H_ */

@@ -1,0 +1,116 @@
+// K4: multiview bilinear feature + RGB lookup -> view tokens.
+//
+// Replaces SpatialEncoder.index / grid_sample (lib/encoder.py:12-62, 225-253) and the RGB
+// append with its 4-frequency code (lib/skinnning_batch.py:428-435).  Semantics: bilinear,
+// align_corners=True, weights from the unclamped corners, indices clamped (border padding).
+// One warp per (point, view): the latent is NHWC so the 128 channels of a tap are one
+// coalesced 512-byte row (a float4 per lane); the 4 taps are independent 128-bit loads.
+#include "common.cuh"
+
+namespace mps {
+
+constexpr int kK4Threads = 256;
+
+struct Taps {
+  int o00, o01, o10, o11;      // pixel offsets (y*W + x) of nw, ne, sw, se
+  float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ Taps make_taps(float u, float v, int img_w, int img_h, int IW, int IH) {
+  // uv -> [-1,1] -> source pixel, exactly the reference's sequence (encoder.py:239, :19-20)
+  const float gx = 2.0f * u / (float)img_w - 1.0f;
+  const float gy = 2.0f * v / (float)img_h - 1.0f;
+  const float ix = ((gx + 1.0f) / 2.0f) * (float)(IW - 1);
+  const float iy = ((gy + 1.0f) / 2.0f) * (float)(IH - 1);
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+  Taps t;
+  t.w00 = (x1 - ix) * (y1 - iy);
+  t.w01 = (ix - x0) * (y1 - iy);
+  t.w10 = (x1 - ix) * (iy - y0);
+  t.w11 = (ix - x0) * (iy - y0);
+  const float fw = (float)(IW - 1), fh = (float)(IH - 1);
+  const int cx0 = (int)fminf(fmaxf(x0, 0.f), fw), cx1 = (int)fminf(fmaxf(x1, 0.f), fw);
+  const int cy0 = (int)fminf(fmaxf(y0, 0.f), fh), cy1 = (int)fminf(fmaxf(y1, 0.f), fh);
+  t.o00 = cy0 * IW + cx0; t.o01 = cy0 * IW + cx1;
+  t.o10 = cy1 * IW + cx0; t.o11 = cy1 * IW + cx1;
+  return t;
+}
+
+__device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, const float4& c, const float4& d, const Taps& t) {
+  float4 r;
+  r.x = a.x * t.w00 + b.x * t.w01 + c.x * t.w10 + d.x * t.w11;
+  r.y = a.y * t.w00 + b.y * t.w01 + c.y * t.w10 + d.y * t.w11;
+  r.z = a.z * t.w00 + b.z * t.w01 + c.z * t.w10 + d.z * t.w11;
+  r.w = a.w * t.w00 + b.w * t.w01 + c.w * t.w10 + d.w * t.w11;
+  return r;
+}
+
+__global__ void __launch_bounds__(kK4Threads)
+gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */, int V, const mpsnerf_frame* __restrict__ frame,
+                     const float* __restrict__ latent, const float* __restrict__ img4, float* __restrict__ tokens, int ld) {
+  const int img_w = frame->img_w, img_h = frame->img_h, FW = frame->feat_w, FH = frame->feat_h;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kK4Threads + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kK4Threads) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int v = (int)(row % V);
+    const float u_ = __ldg(&uv[2 * row]), v_ = __ldg(&uv[2 * row + 1]);
+    float* out = tokens + row * ld;
+    // latent: 128 channels, 4 per lane
+    {
+      const Taps t = make_taps(u_, v_, img_w, img_h, FW, FH);
+      const float4* base = reinterpret_cast<const float4*>(latent + (size_t)v * FH * FW * 128) + lane;
+      const float4 a = __ldg(base + (size_t)t.o00 * 32), b = __ldg(base + (size_t)t.o01 * 32);
+      const float4 c = __ldg(base + (size_t)t.o10 * 32), d = __ldg(base + (size_t)t.o11 * 32);
+      const float4 r = lerp4(a, b, c, d, t);
+      if ((ld & 3) == 0) {
+        reinterpret_cast<float4*>(out)[lane] = r;
+      } else {
+        out[4 * lane] = r.x; out[4 * lane + 1] = r.y; out[4 * lane + 2] = r.z; out[4 * lane + 3] = r.w;
+      }
+    }
+    // rgb: 27-wide code [x, sin(f0 x), cos(f0 x), ...] with cos as sin(. + fl(pi/2)) (run_nerf_helpers.py:337-353)
+    {
+      const Taps t = make_taps(u_, v_, img_w, img_h, img_w, img_h);
+      const float4* base = reinterpret_cast<const float4*>(img4 + (size_t)v * img_h * img_w * 4);
+      const float4 r = lerp4(__ldg(base + t.o00), __ldg(base + t.o01), __ldg(base + t.o10), __ldg(base + t.o11), t);
+      // lane l < 27: element e = l; e<3: identity; else k=(e-3)/6, within=(e-3)%6, ch=within%3, cos=within>=3
+      if (lane < 27) {
+        const int e = lane;
+        const int ch = (e < 3) ? e : ((e - 3) % 3);
+        const float x = ch == 0 ? r.x : (ch == 1 ? r.y : r.z);
+        float val = x;
+        if (e >= 3) {
+          const int k = (e - 3) / 6;
+          const bool is_cos = ((e - 3) % 6) >= 3;
+          const float f = 3.14159265358979323846f * (float)(1 << k);
+          val = sinf(fmaf(x, f, is_cos ? 1.57079632679489661923f : 0.0f));
+        }
+        out[128 + e] = val;
+      } else if (128 + lane < ld) {
+        out[128 + lane] = 0.f;           // pad columns 155.. (ld <= 160)
+      }
+    }
+  }
+}
+
+}  // namespace mps
+
+extern "C" int mpsnerf_gather_tokens(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
+                                     const float* latent, const float* img4, float* tokens, int32_t ld,
+                                     void* stream) {
+  MPS_REQUIRE(count >= 0 && n_views >= 1 && n_views <= MPSNERF_MAX_VIEWS);
+  if (count == 0) return MPSNERF_OK;
+  MPS_REQUIRE(uv && frame && latent && img4 && tokens);
+  MPS_REQUIRE(ld >= MPSNERF_TOKEN_DIM && ld <= MPSNERF_TOKEN_LD);
+  MPS_REQUIRE((reinterpret_cast<uintptr_t>(latent) & 15) == 0 && (reinterpret_cast<uintptr_t>(img4) & 15) == 0);
+  MPS_REQUIRE((reinterpret_cast<uintptr_t>(tokens) & 15) == 0);
+  const int64_t rows = count * n_views;
+  int64_t blocks = (rows * 32 + mps::kK4Threads - 1) / mps::kK4Threads;
+  if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
+  mps::gather_tokens_kernel<<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
+      uv, rows, n_views, frame, latent, img4, tokens, ld);
+  MPS_LAUNCH_CHECK();
+  return MPSNERF_OK;
+}

@@ -1,0 +1,155 @@
+// K1: stratified sampling + world->SMPL + human-region mask + nearest posed vertex + compaction.
+//
+// One thread per sample point, 256 points per block iteration, three phases:
+//   1. every thread generates its point, moves it to SMPL space (pinned fp32) and tests one
+//      bit of the dilated occupancy bitmap; survivors are compacted into a candidate list;
+//   2. the candidate list is processed densely (one thread per candidate) with the exact
+//      27-cell search -- this keeps warps full although only ~15% of the points of a frame
+//      are candidates;
+//   3. every thread writes the per-point outputs of its own point and the active points are
+//      compacted into the global active list (one atomicAdd per block).
+#include "grid.cuh"
+
+namespace mps {
+
+constexpr int kK1Threads = 256;
+
+__global__ void __launch_bounds__(kK1Threads)
+sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const float* __restrict__ t_vals,
+                  const float* __restrict__ u, const float* __restrict__ points,
+                  const mpsnerf_frame* __restrict__ frame, const char* __restrict__ grid_buf,
+                  float* __restrict__ raw, float* __restrict__ pts_mask, float* __restrict__ smpl_query,
+                  float* __restrict__ smpl_src, int32_t* __restrict__ act_pid, int32_t* __restrict__ act_idx2,
+                  float* __restrict__ act_q, int32_t* __restrict__ act_count) {
+  const GridView g = grid_view(grid_buf);
+  __shared__ GridHdr s_hdr;
+  __shared__ float s_fr[12];                 // Th(3) R(9)
+  __shared__ float s_q[kK1Threads * 3];
+  __shared__ float s_d2[kK1Threads];
+  __shared__ int s_idx[kK1Threads];
+  __shared__ int s_cand[kK1Threads];
+  __shared__ int s_warp_cnt[kK1Threads / 32];
+  __shared__ int s_ncand, s_nact, s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_hdr = *g.hdr;
+  if (tid < 3) s_fr[tid] = frame->Th_tp[tid];
+  if (tid >= 3 && tid < 12) s_fr[tid] = frame->R_tp[tid - 3];
+  __syncthreads();
+  const GridHdr h = s_hdr;
+  const float INF = __int_as_float(0x7f800000);
+
+  for (int64_t base = (int64_t)blockIdx.x * kK1Threads; base < n_points; base += (int64_t)gridDim.x * kK1Threads) {
+    const int64_t pid = base + tid;
+    const bool valid = pid < n_points;
+    // ---- phase 1
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    bool cand = false;
+    if (valid) {
+      float px, py, pz;
+      if (points != nullptr) {
+        px = points[3 * pid]; py = points[3 * pid + 1]; pz = points[3 * pid + 2];
+      } else {
+        const int64_t r = pid / S;
+        const int s = (int)(pid - r * S);
+        const float* ray = rays + 8 * r;
+        const float z = sample_z(ray[6], ray[7], t_vals, s, S, u ? u + r * S : nullptr);
+        px = padd(ray[0], pmul(ray[3], z));     // run_nerf_batch.py:424
+        py = padd(ray[1], pmul(ray[4], z));
+        pz = padd(ray[2], pmul(ray[5], z));
+      }
+      const float d0 = psub(px, s_fr[0]), d1 = psub(py, s_fr[1]), d2 = psub(pz, s_fr[2]);
+      qx = padd(padd(pmul(d0, s_fr[3]), pmul(d1, s_fr[6])), pmul(d2, s_fr[9]));   // (p-Th)@R, :347
+      qy = padd(padd(pmul(d0, s_fr[4]), pmul(d1, s_fr[7])), pmul(d2, s_fr[10]));
+      qz = padd(padd(pmul(d0, s_fr[5]), pmul(d1, s_fr[8])), pmul(d2, s_fr[11]));
+      cand = grid_maybe_near(h, g.occ, cell_coord(qx, h.ox, h.inv_cell), cell_coord(qy, h.oy, h.inv_cell),
+                             cell_coord(qz, h.oz, h.inv_cell));
+    }
+    s_q[3 * tid] = qx; s_q[3 * tid + 1] = qy; s_q[3 * tid + 2] = qz;
+    s_d2[tid] = INF;
+    s_idx[tid] = -1;
+    unsigned bal = __ballot_sync(0xffffffffu, cand);
+    if (lane == 0) s_warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    {
+      int off = 0;
+      for (int w = 0; w < wid; ++w) off += s_warp_cnt[w];
+      if (cand) s_cand[off + __popc(bal & ((1u << lane) - 1))] = tid;
+      if (tid == kK1Threads - 1) s_ncand = off + __popc(bal);
+    }
+    __syncthreads();
+    // ---- phase 2 (dense over candidates)
+    const int ncand = s_ncand;
+    if (tid < ncand) {
+      const int t = s_cand[tid];
+      const float cxq = s_q[3 * t], cyq = s_q[3 * t + 1], czq = s_q[3 * t + 2];
+      float bd2 = INF;
+      int bidx = 0x7fffffff;
+      nn_search27(h, g.cell_start, g.sorted, cell_coord(cxq, h.ox, h.inv_cell), cell_coord(cyq, h.oy, h.inv_cell),
+                  cell_coord(czq, h.oz, h.inv_cell), cxq, cyq, czq, bd2, bidx);
+      s_d2[t] = bd2;
+      s_idx[t] = bidx;
+    }
+    __syncthreads();
+    // ---- phase 3
+    const bool active = valid && (s_d2[tid] < kMaskThresh);     // lib/skinnning_batch.py:360-361
+    bal = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) s_warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < wid; ++w) off += s_warp_cnt[w];
+    if (tid == kK1Threads - 1) {
+      const int n = off + __popc(bal);
+      s_nact = n;
+      s_base = n ? atomicAdd(act_count, n) : 0;
+    }
+    __syncthreads();
+    if (active) {
+      const int64_t slot = (int64_t)s_base + off + __popc(bal & ((1u << lane) - 1));
+      act_pid[slot] = (int32_t)pid;
+      act_idx2[slot] = s_idx[tid];
+      act_q[3 * slot] = qx; act_q[3 * slot + 1] = qy; act_q[3 * slot + 2] = qz;
+    }
+    if (valid) {
+      pts_mask[pid] = active ? 1.0f : 0.0f;
+      if (!active) reinterpret_cast<float4*>(raw)[pid] = make_float4(-80.f, -80.f, -80.f, -80.f);   // :493
+    }
+    // smpl_query / smpl_src rows (ref :483-484): staged so that the stores are 128-bit and coalesced
+    if (!active) { s_q[3 * tid] = 0.f; s_q[3 * tid + 1] = 0.f; s_q[3 * tid + 2] = 0.f; }
+    __syncthreads();
+    if (base + kK1Threads <= n_points) {
+      if (tid < kK1Threads * 3 / 4) {
+        reinterpret_cast<float4*>(smpl_query + 3 * base)[tid] = reinterpret_cast<const float4*>(s_q)[tid];
+        reinterpret_cast<float4*>(smpl_src + 3 * base)[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else if (valid) {
+      for (int k = 0; k < 3; ++k) { smpl_query[3 * pid + k] = s_q[3 * tid + k]; smpl_src[3 * pid + k] = 0.f; }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mps
+
+extern "C" int mpsnerf_sample_knn(const float* rays, int64_t n_rays, int32_t S, const float* t_vals,
+                                  const float* u, const float* points, const mpsnerf_frame* frame,
+                                  const void* grid_tp, float* raw, float* pts_mask, float* smpl_query,
+                                  float* smpl_src, int32_t* act_pid, int32_t* act_idx2, float* act_q,
+                                  int32_t* act_count, void* stream) {
+  MPS_REQUIRE(n_rays >= 0 && S >= 1);
+  const int64_t P = n_rays * S;
+  MPS_REQUIRE(P < ((int64_t)1 << 31));
+  if (P == 0) return MPSNERF_OK;
+  MPS_REQUIRE(points != nullptr || (rays != nullptr && t_vals != nullptr));
+  MPS_REQUIRE(frame && grid_tp && raw && pts_mask && smpl_query && smpl_src);
+  MPS_REQUIRE(act_pid && act_idx2 && act_q && act_count);
+  MPS_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+  MPS_REQUIRE((reinterpret_cast<uintptr_t>(smpl_query) & 15) == 0 && (reinterpret_cast<uintptr_t>(smpl_src) & 15) == 0);
+  int64_t blocks = (P + mps::kK1Threads - 1) / mps::kK1Threads;
+  if (blocks > mps::kNumSMs * 8) blocks = mps::kNumSMs * 8;
+  mps::sample_knn_kernel<<<(int)blocks, mps::kK1Threads, 0, (cudaStream_t)stream>>>(
+      rays, P, S, t_vals, u, points, frame, static_cast<const char*>(grid_tp), raw, pts_mask, smpl_query,
+      smpl_src, act_pid, act_idx2, act_q, act_count);
+  MPS_LAUNCH_CHECK();
+  return MPSNERF_OK;
+}

@@ -1,0 +1,302 @@
+"""Render engine: per-frame preparation and kernel orchestration over the C ABI.
+
+This is the host side of the hot path.  Per ``render()`` call it
+  1. computes the per-frame constants (LBS transforms for target / big / source pose,
+     cameras) once -- the reference recomputes them 4x per chunk
+     (lib/skinnning_batch.py:206,243,266,289);
+  2. runs the encoder trunk once and lays its output out NHWC -- the reference re-runs it
+     per chunk (lib/skinnning_batch.py:350-351);
+  3. builds the two exact nearest-vertex grids (posed vertices in SMPL space, template);
+  4. launches K1 (sample + mask + argmin + compaction) over all rays, reads the active count
+     (the only host sync of a frame), then K3/K4/K5 over slabs of active points and K6.
+All per-point arithmetic happens in libmpsnerf_b200.so; torch is used for memory, streams
+and the cuDNN encoder trunk only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .lib.run_nerf_helpers import get_transform_params_torch
+
+GRID_CELL_TARGET = 0.0505      # >= 1.01 * 0.05 m: makes the 27-cell search exact for the mask radius
+GRID_CELL_TEMPLATE = 0.06
+
+# order of the host pointer table taken by mpsnerf_dense_fp32
+DENSE_FP32_ORDER = (
+    [f"transformer.layers.{l}.{k}" for l in range(2) for k in (
+        "0.fn.norm.weight", "0.fn.norm.bias", "0.fn.fn.to_qkv.weight", "0.fn.fn.to_out.0.weight",
+        "0.fn.fn.to_out.0.bias", "1.fn.norm.weight", "1.fn.norm.bias", "1.fn.fn.net.0.weight",
+        "1.fn.fn.net.0.bias", "1.fn.fn.net.3.weight", "1.fn.fn.net.3.bias")]
+    + [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")]
+    + ["alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight", "feature_linear.bias",
+       "views_linear.weight", "views_linear.bias", "rgb_linear.weight", "rgb_linear.bias"])
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pack_kmajor_sw128(w, n_pad=None, k_pad=None):
+    """Pack a (N,K) weight into the K-major SWIZZLE_128B chunk layout of csrc/umma.cuh.
+
+    Returns a uint8 tensor of (K_pad/64) chunks x N_pad rows x 128 bytes: bf16, the 16-byte
+    unit j of row r stored at unit (j ^ (r & 7)) of that row.  Pure index arithmetic, so it
+    runs on any device; checked on CPU against the address formula in tests/test_packing.py.
+    """
+    N, K = w.shape
+    n_pad = n_pad or ((N + 15) // 16) * 16
+    k_pad = k_pad or ((K + 63) // 64) * 64
+    wp = torch.zeros(n_pad, k_pad, dtype=torch.bfloat16, device=w.device)
+    wp[:N, :K] = w.to(torch.bfloat16)
+    t = wp.reshape(n_pad, k_pad // 64, 8, 8)                       # (row, chunk, unit, elem)
+    r7 = (torch.arange(n_pad, device=w.device) & 7)[:, None]
+    src_unit = torch.arange(8, device=w.device)[None, :] ^ r7      # stored unit u holds logical unit u ^ r7
+    t = torch.gather(t, 2, src_unit[:, None, :, None].expand(n_pad, k_pad // 64, 8, 8))
+    return t.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)
+
+
+class FrameContext:
+    """Device-resident state of one (source, target) pair."""
+    __slots__ = ("frame_dev", "grid_tp", "grid_tv", "latent", "img4", "skin_w", "n_views", "keep")
+
+
+class RenderEngine:
+    def __init__(self, net, precision="fp32", slab=None):
+        assert precision in ("fp32", "bf16")
+        self.net = net
+        self.precision = precision
+        self.slab = slab or (32768 if precision == "fp32" else 262144)
+        self.lib = _lib.load()
+        self._ws = {}
+        self._packed = None
+        self._packed_key = None
+        self.debug = None            # set to a dict to capture per-stage tensors (tests)
+        self.timers = None           # set to a dict to record CUDA-event pairs per stage (bench.py)
+        self.last_active = 0
+
+    class _Span:
+        def __init__(self, eng, name):
+            self.eng, self.name = eng, name
+
+        def __enter__(self):
+            if self.eng.timers is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.eng.timers is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.eng.timers.setdefault(self.name, []).append((self.e0, e1))
+
+    def span(self, name):
+        return RenderEngine._Span(self, name)
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name, nbytes, device):
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes or t.device != device:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._ws[name] = t
+        return t
+
+    def _weights_fp32(self):
+        sd = dict(self.net.named_parameters())
+        tensors = [sd[k].detach() for k in DENSE_FP32_ORDER]
+        for t in tensors:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        table = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return table, tensors
+
+    # ------------------------------------------------------------------ per-frame preparation
+    @torch.no_grad()
+    def prepare_frame(self, sp, tp, smpl):
+        """sp/tp: squeezed input dicts on the CUDA device; smpl: CPU tensor dict of the gender."""
+        with self.span("prep"):
+            return self._prepare_frame(sp, tp, smpl)
+
+    def _prepare_frame(self, sp, tp, smpl):
+        dev = sp["img_all"].device
+        lib = self.lib
+        V = sp["img_all"].shape[0]
+        assert 2 <= V <= _lib.MAX_VIEWS
+        # one D2H of the small per-frame parameters
+        flat = torch.cat([tp["params"]["poses"].reshape(-1), tp["params"]["shapes"].reshape(-1),
+                          tp["params"]["R"].reshape(-1), tp["params"]["Th"].reshape(-1),
+                          sp["params"]["poses"].reshape(-1), sp["params"]["shapes"].reshape(-1),
+                          sp["params"]["R"].reshape(-1), sp["params"]["Th"].reshape(-1),
+                          sp["R_all"].reshape(-1), sp["T_all"].reshape(-1), sp["K_all"].reshape(-1)]).float().cpu()
+        o = 0
+
+        def take(n):
+            nonlocal o
+            v = flat[o:o + n]
+            o += n
+            return v
+
+        def params():
+            return {"poses": take(72).reshape(1, 72), "shapes": take(10).reshape(1, 10), "R": take(9).reshape(3, 3),
+                    "Th": take(3).reshape(1, 3)}
+
+        tpp, spp = params(), params()
+        cam_R, cam_T, cam_K = take(9 * V), take(3 * V), take(9 * V)
+        big = torch.zeros(1, 72)                                     # lib/skinnning_batch.py:193-201
+        big[0, 5], big[0, 8], big[0, 23], big[0, 26] = np.pi / 4, -np.pi / 4, -np.pi / 6, np.pi / 6
+
+        def A12(poses, shapes):
+            A = get_transform_params_torch(smpl, {"poses": poses, "shapes": shapes, "R": None, "Th": None})[0]
+            return A[:, :3, :].reshape(-1).numpy()
+
+        fr = _lib.Frame()
+        fr.Th_tp[:] = tpp["Th"].reshape(-1).tolist()
+        fr.R_tp[:] = tpp["R"].reshape(-1).tolist()
+        fr.Rinv_sp[:] = torch.inverse(spp["R"]).reshape(-1).tolist()
+        fr.Th_sp[:] = spp["Th"].reshape(-1).tolist()
+        fr.A_tp[:] = A12(tpp["poses"], tpp["shapes"]).tolist()
+        fr.A_big_tp[:] = A12(big, tpp["shapes"]).tolist()
+        fr.A_big_sp[:] = A12(big, spp["shapes"]).tolist()
+        fr.A_sp[:] = A12(spp["poses"], spp["shapes"]).tolist()
+        fr.cam_R[:9 * V] = cam_R.tolist()
+        fr.cam_T[:3 * V] = cam_T.tolist()
+        fr.cam_K[:9 * V] = cam_K.tolist()
+        H, W = sp["img_all"].shape[-2:]
+        fr.n_views, fr.img_w, fr.img_h = V, W, H
+
+        ctx = FrameContext()
+        ctx.n_views = V
+        # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
+        latent = self.net.encoder_2d(sp["img_all"])
+        fr.feat_w, fr.feat_h = latent.shape[-1], latent.shape[-2]
+        ctx.latent = latent.permute(0, 2, 3, 1).contiguous().float()
+        ctx.img4 = F.pad(sp["img_all"].permute(0, 2, 3, 1), (0, 1)).contiguous().float()
+        host = torch.frombuffer(bytearray(bytes(fr)), dtype=torch.uint8)
+        ctx.frame_dev = host.to(dev)
+        ctx.skin_w = smpl["weights"].to(dev).float().contiguous()
+        ctx.keep = (fr,)
+
+        nv = tp["vertices"].shape[0]
+        gb = lib.mpsnerf_grid_bytes(nv)
+        ctx.grid_tp = torch.empty(gb, dtype=torch.uint8, device=dev)
+        ctx.grid_tv = torch.empty(gb, dtype=torch.uint8, device=dev)
+        verts = tp["vertices"].float().contiguous()
+        tverts = sp["t_vertices"].float().contiguous()
+        fptr = ctx.frame_dev.data_ptr()
+        _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, ctypes.c_void_p(fptr + _lib.Frame.Th_tp.offset),
+                                          ctypes.c_void_p(fptr + _lib.Frame.R_tp.offset), GRID_CELL_TARGET,
+                                          _lib.ptr(ctx.grid_tp), gb, _stream()), "grid_build(target)")
+        _lib.check(lib.mpsnerf_grid_build(_lib.ptr(tverts), tverts.shape[0], None, None, GRID_CELL_TEMPLATE,
+                                          _lib.ptr(ctx.grid_tv), gb, _stream()), "grid_build(template)")
+        _lib.count_launches(2)
+        return ctx
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.no_grad()
+    def run(self, ctx, rays8=None, S=1, t_vals=None, u=None, points=None, composite=True, occupancy=False,
+            all_active=False):
+        """rays8 (N,8) [o,d,near,far] or points (P,3).  Returns a dict of flat tensors."""
+        lib, dev = self.lib, ctx.latent.device
+        if points is not None:
+            P, N = points.shape[0], points.shape[0]
+            S = 1
+        else:
+            N = rays8.shape[0]
+            P = N * S
+        V = ctx.n_views
+        raw = torch.empty(P, 4, device=dev)
+        mask = torch.empty(P, device=dev)
+        sq = torch.empty(P, 3, device=dev)
+        ss = torch.empty(P, 3, device=dev)
+        out = {"raw": raw, "pts_mask": mask, "smpl_query_pts": sq, "smpl_src_pts": ss}
+        if P == 0:
+            return out
+        act_pid = self._buf("act_pid", 4 * P, dev).view(torch.int32)
+        act_idx2 = self._buf("act_idx2", 4 * P, dev).view(torch.int32)
+        act_q = self._buf("act_q", 12 * P, dev).view(torch.float32)
+        counter = self._buf("counter", 256, dev).view(torch.int32)
+        if all_active:      # extract_mesh: every point is evaluated, canonical = the point itself
+            act_pid[:P] = torch.arange(P, device=dev, dtype=torch.int32)
+            act_q[:3 * P] = points.reshape(-1)
+            mask.fill_(1.0)
+            sq.zero_()
+            ss.zero_()
+            n_act = P
+        else:
+            counter[:1].zero_()
+            with self.span("k1_sample_knn"):
+              _lib.check(lib.mpsnerf_sample_knn(
+                _lib.ptr(rays8), N, S, _lib.ptr(t_vals), _lib.ptr(u), _lib.ptr(points), _lib.ptr(ctx.frame_dev),
+                _lib.ptr(ctx.grid_tp), _lib.ptr(raw), _lib.ptr(mask), _lib.ptr(sq), _lib.ptr(ss), _lib.ptr(act_pid),
+                _lib.ptr(act_idx2), _lib.ptr(act_q), _lib.ptr(counter), _stream()), "sample_knn")
+            _lib.count_launches(1)
+            n_act = int(counter[0].item())          # the one host sync of the frame
+        out["n_active"] = n_act
+        self.last_active = n_act
+        dbg = self.debug
+        if dbg is not None:
+            dbg.update(act_pid=act_pid[:n_act].clone(), act_idx2=act_idx2[:n_act].clone(),
+                       act_q=act_q[:3 * n_act].reshape(-1, 3).clone(), xc=[], idx3=[], xw=[], uv=[], tokens=[])
+        ld = _lib.TOKEN_DIM if self.precision == "fp32" else _lib.TOKEN_LD
+        slab = self.slab
+        if n_act:
+            cap = min(slab, n_act)
+            xc = self._buf("xc", 12 * cap, dev).view(torch.float32)
+            uv = self._buf("uv", 8 * V * cap, dev).view(torch.float32)
+            tokens = self._buf("tokens", 4 * ld * V * cap, dev).view(torch.float32)
+            if self.precision == "fp32":
+                wtable, keep = self._weights_fp32()
+                ws = self._buf("dense", lib.mpsnerf_dense_fp32_workspace(cap, V), dev)
+            else:
+                packed = self._packed_weights(dev)
+                ws = self._buf("dense", lib.mpsnerf_dense_bf16_workspace(cap, V), dev)
+            idx3 = self._buf("idx3", 4 * cap, dev).view(torch.int32) if dbg is not None else None
+            xw = self._buf("xw", 12 * cap, dev).view(torch.float32) if dbg is not None else None
+        for first in range(0, n_act, slab):
+            cnt = min(slab, n_act - first)
+            with self.span("k3_deform"):
+              _lib.check(lib.mpsnerf_deform_project(
+                _lib.ptr(act_pid), _lib.ptr(act_idx2), _lib.ptr(act_q), first, cnt, _lib.ptr(ctx.skin_w),
+                _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.grid_tv), _lib.ptr(xc), _lib.ptr(uv), _lib.ptr(ss),
+                _lib.ptr(idx3), _lib.ptr(xw), 1 if all_active else 0, _stream()), "deform_project")
+            with self.span("k4_gather"):
+              _lib.check(lib.mpsnerf_gather_tokens(_lib.ptr(uv), cnt, V, _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.latent),
+                                                 _lib.ptr(ctx.img4), _lib.ptr(tokens), ld, _stream()), "gather_tokens")
+            if self.precision == "fp32":
+              with self.span("dense"):
+                _lib.check(lib.mpsnerf_dense_fp32(_lib.ptr(tokens), ld, _lib.ptr(xc), cnt, V, wtable, _lib.ptr(act_pid),
+                                                  first, _lib.ptr(raw), _lib.ptr(ws), _stream()), "dense_fp32")
+                _lib.count_launches(2 + 30)
+            else:
+              with self.span("dense"):
+                _lib.check(lib.mpsnerf_dense_bf16(_lib.ptr(tokens), ld, _lib.ptr(xc), cnt, V, _lib.ptr(packed),
+                                                  packed.numel(), _lib.ptr(act_pid), first, _lib.ptr(raw),
+                                                  _lib.ptr(ws), _stream()), "dense_bf16")
+                _lib.count_launches(2 + 2)
+            if dbg is not None:
+                dbg["xc"].append(xc[:3 * cnt].reshape(-1, 3).clone())
+                dbg["idx3"].append(idx3[:cnt].clone())
+                dbg["xw"].append(xw[:3 * cnt].reshape(-1, 3).clone())
+                dbg["uv"].append(uv[:2 * V * cnt].reshape(-1, V, 2).clone())
+                dbg["tokens"].append(tokens[:ld * V * cnt].reshape(-1, V, ld).clone())
+        if composite and points is None:
+            rgb = torch.empty(N, 3, device=dev)
+            disp = torch.empty(N, device=dev)
+            acc = torch.empty(N, device=dev)
+            depth = torch.empty(N, device=dev)
+            with self.span("k6_composite"):
+              _lib.check(lib.mpsnerf_composite(_lib.ptr(raw), _lib.ptr(rays8), N, S, _lib.ptr(t_vals), _lib.ptr(u), None,
+                                             1 if occupancy else 0, _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc),
+                                             _lib.ptr(depth), None, None, _stream()), "composite")
+            _lib.count_launches(1)
+            out.update(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth)
+        return out
+
+    def _packed_weights(self, dev):
+        from .pack import pack_weights_bf16
+        key = tuple(p._version for p in self.net.parameters())
+        if self._packed is None or key != self._packed_key or self._packed.device != dev:
+            self._packed = pack_weights_bf16(self.net, dev)
+            self._packed_key = key
+        return self._packed

@@ -1,0 +1,177 @@
+"""SKinningBatch: the reference's network class, served by the CUDA hot path.
+
+Same constructor signature, attributes and state-dict keys as the reference
+(``lib/skinnning_batch.py:109-164``), so ``model_selection.return_model`` and checkpoints
+(``ckpt['network_fn_state_dict']``) work unchanged.  ``forward`` keeps the reference
+contract (``:333-514``): ``(sp_input, tp_input, world_query_pts (1,N,3), viewdir) ->
+raw (1,N,17)`` -- but runs K1/K3/K4/K5 of libmpsnerf_b200.so instead of torch ops, and never
+mutates the caller's dicts.  Supported configuration = the shipped configs
+(``human_sample=1, use_trans=1, append_rgb=1, with_viewdirs=0, mean_shape=0,
+correction_field=0, skinning_field=0``); anything else raises NotImplementedError.
+There is no CPU path: inputs must live on a CUDA device.
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .base_utils import read_pickle
+from .encoder import SparseConvNet, SpatialEncoder
+from .run_nerf_helpers import PositionalEncoding, SMPL_to_tensor, sequeeze_0
+from .transformer import Transformer
+
+_DEFAULT_SMPL = None
+
+
+def set_default_smpl_models(models):
+    """Provide SMPL dicts ({'male','female','neutral'} or a single dict) instead of ./assets/*.pkl.
+
+    The licensed pickles cannot be shipped; tests and benchmarks inject the synthetic
+    SMPL-shaped body of ``mpsnerf_b200.synthetic.make_smpl`` through this hook.
+    """
+    global _DEFAULT_SMPL
+    _DEFAULT_SMPL = models
+
+
+class DeformField(nn.Module):
+    """Parameter-compatible with the reference (lib/skinnning_batch.py:77-106); dead under the
+    shipped configs, kept so that checkpoints load."""
+
+    def __init__(self, D=8, W=256, input_ch=3, output_ch=3, skips=(4,), deform_type="weights"):
+        super().__init__()
+        self.skips = list(skips)
+        self.pts_time_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] + [nn.Linear(W + input_ch if i in self.skips else W, W) for i in range(D - 1)])
+        self.output_linear = nn.Linear(W, output_ch)
+        if deform_type == "correction":
+            nn.init.constant_(self.output_linear.weight, 0)
+            nn.init.constant_(self.output_linear.bias, 0)
+        self.deform_type = deform_type
+
+    def forward(self, x):
+        h = x
+        for i, lin in enumerate(self.pts_time_linears):
+            h = F.relu(lin(h))
+            if i in self.skips:
+                h = torch.cat([x, h], -1)
+        out = self.output_linear(h)
+        return F.softmax(out, dim=1) if self.deform_type == "weights" else out
+
+
+def _load_smpl():
+    if _DEFAULT_SMPL is not None:
+        m = _DEFAULT_SMPL
+        if "v_template" in m:
+            m = {"male": m, "female": m, "neutral": m}
+        return {k: SMPL_to_tensor(dict(v)) for k, v in m.items()}
+    paths = {"male": "basicmodel_m_lbs_10_207_0_v1.0.0.pkl", "female": "basicmodel_f_lbs_10_207_0_v1.0.0.pkl",
+             "neutral": "SMPL_NEUTRAL.pkl"}
+    out = {}
+    for k, f in paths.items():
+        p = os.path.join("assets", f)
+        if not os.path.exists(p):
+            raise FileNotFoundError(f"{p} not found: place the licensed SMPL models under ./assets "
+                                    "(as the reference requires) or call set_default_smpl_models()")
+        out[k] = SMPL_to_tensor(read_pickle(p))
+    return out
+
+
+class SKinningBatch(nn.Module):
+    def __init__(self, use_agg=False, human_sample=True, density_loss=False, with_viewdirs=False, use_f2d=True,
+                 use_trans=False, smooth_loss=False, num_instances=1, mean_shape=1, correction_field=1,
+                 skinning_field=1, data_set_type="H36M_B", append_rgb="False", precision=None):
+        super().__init__()
+        self.encoder_3d = SparseConvNet(num_layers=2)
+        self.encoder_2d = SpatialEncoder(num_layers=2)
+        self.forward_deform = DeformField(D=2, input_ch=39 + 32 + 128, output_ch=3, deform_type="correction")
+        self.backward_deform = DeformField(D=4, input_ch=39 + 128, output_ch=24, deform_type="weights")
+        self.with_viewdirs = with_viewdirs
+        self.pos_enc = PositionalEncoding(num_freqs=6)
+        self.view_enc = PositionalEncoding(num_freqs=4)
+        smpl = _load_smpl()
+        self.SMPL_MALE, self.SMPL_FEMALE, self.SMPL_NEU = smpl["male"], smpl["female"], smpl["neutral"]
+        self.SMPL_NEUTRAL = self.SMPL_NEU
+        self.faces = self.SMPL_NEUTRAL["f"]
+        W = 256
+        self.skips = [4]
+        nerf_in = (39 + 128 + 27) if append_rgb else (39 + 128)
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(nerf_in, W)] + [nn.Linear(W + nerf_in if i in self.skips else W, W) for i in range(7)])
+        self.alpha_linear = nn.Linear(W, 1)
+        self.feature_linear = nn.Linear(W, W)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+        nerf_in2 = (128 + 256 + 27) if append_rgb else 384
+        self.views_linear = nn.Linear(nerf_in2 + 27 if with_viewdirs else nerf_in2, W // 2)
+        self.transformer = Transformer(128 + 27 if append_rgb else 128) if use_trans else None
+        self.latent_codes = nn.Embedding(num_instances, 128)
+        nn.init.normal_(self.latent_codes.weight, mean=0, std=0.01)
+        self.extract_mesh = False
+        self.mesh_animation = False
+        self.use_agg, self.data_set_type, self.human_sample = use_agg, data_set_type, human_sample
+        self.density_loss, self.use_f2d, self.use_trans, self.smooth_loss = density_loss, use_f2d, use_trans, smooth_loss
+        self.mean_shape, self.correction_field, self.skinning_field = mean_shape, correction_field, skinning_field
+        self.append_rgb = append_rgb
+        self.precision = precision or os.environ.get("MPSNERF_PRECISION", "bf16")
+        self._engine = None
+        self._frame_key = None
+        self._frame_ctx = None
+
+    # ------------------------------------------------------------------ reference API
+    def set_extract_mesh(self, flag):
+        self.extract_mesh = flag
+
+    def _check_supported(self):
+        bad = []
+        if not self.human_sample: bad.append("human_sample=0")
+        if not self.use_trans: bad.append("use_trans=0")
+        if not self.append_rgb: bad.append("append_rgb=0")
+        if self.with_viewdirs: bad.append("with_viewdirs=1")
+        if self.mean_shape: bad.append("mean_shape=1")
+        if self.correction_field or self.skinning_field: bad.append("correction_field/skinning_field=1")
+        if self.mesh_animation: bad.append("mesh_animation")
+        if bad:
+            raise NotImplementedError("mpsnerf_b200 implements the shipped-config hot path only; unsupported: "
+                                      + ", ".join(bad))
+
+    def engine(self):
+        if self._engine is None or self._engine.precision != self.precision:
+            from ..engine import RenderEngine
+            self._engine = RenderEngine(self, precision=self.precision)
+        return self._engine
+
+    def _smpl_for(self, gender):
+        g = int(gender.reshape(-1)[0].item()) if torch.is_tensor(gender) else int(gender)
+        return self.SMPL_MALE if g == 1 else (self.SMPL_FEMALE if g == 0 else self.SMPL_NEU)   # :335-340
+
+    def invalidate_frame_cache(self):
+        self._frame_key = None
+
+    def frame_context(self, sp_input, tp_input):
+        """Prepared per-frame state for already-squeezed dicts, cached on the tensors' identity."""
+        probe = (sp_input["img_all"], sp_input["params"]["poses"], sp_input["t_vertices"], tp_input["vertices"],
+                 tp_input["params"]["poses"], tp_input["params"]["Th"])
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in probe) + (self.training,)
+        if key != self._frame_key:
+            self._check_supported()
+            if not sp_input["img_all"].is_cuda:
+                raise RuntimeError("mpsnerf_b200 has no CPU path: inputs must be CUDA tensors")
+            self._frame_ctx = self.engine().prepare_frame(sp_input, tp_input, self._smpl_for(sp_input["gender"]))
+            self._frame_key = key
+            self._frame_keep = probe
+        return self._frame_ctx
+
+    def forward(self, sp_input, tp_input, world_query_pts, viewdir=None):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("training (backward) through the CUDA hot path is not built yet; "
+                                      "call under torch.no_grad() / eval()")
+        pts = world_query_pts.reshape(-1, 3).float().contiguous()
+        sp, tp = sequeeze_0(sp_input, tp_input) if sp_input["img_all"].dim() == 5 else (sp_input, tp_input)
+        ctx = self.frame_context(sp, tp)
+        res = self.engine().run(ctx, points=pts, composite=False, all_active=bool(self.extract_mesh))
+        if self.extract_mesh:                                   # :478-480
+            return res["raw"].unsqueeze(0)
+        P = pts.shape[0]
+        zeros = torch.zeros(P, 6, device=pts.device)
+        raw = torch.cat([res["raw"], res["pts_mask"][:, None], zeros, res["smpl_query_pts"], res["smpl_src_pts"]], -1)
+        return raw.unsqueeze(0)                                 # (1, P, 17), :494,514

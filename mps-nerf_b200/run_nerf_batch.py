@@ -1,0 +1,207 @@
+"""Render entry points with the reference's names and contracts (run_nerf_batch.py:42-135,
+301-444): ``render``, ``batchify_rays``, ``render_rays``, ``run_network``, ``raw2outputs``,
+``create_nerf``.
+
+Differences that a caller can observe are limited to what SURVEY.md section 8b allows:
+the input dicts are never mutated, the arguments are not parsed at import time (call
+``configure(args)``; defaults = the parser's), and the sampling + network + compositing of
+``render_rays`` run as fused CUDA kernels instead of through ``network_query_fn``.
+Returned ``extras`` hold the same keys/shapes/values; ``correction``/``correction_`` are
+zero tensors (correction_field = 0 in the shipped configs).
+"""
+import ctypes
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .lib.run_nerf_helpers import shifted_softplus, wide_sigmoid, img2mse, mse2psnr, to8b  # noqa: F401 (API)
+from .model_selection import return_model
+from .parser_config import config_parser
+
+global_args = config_parser().parse_args([])
+density_actfn = shifted_softplus
+rgb_actfn = wide_sigmoid
+
+
+def configure(args):
+    """Install the parsed flags (the reference does this at import, run_nerf_batch.py:23-24)."""
+    global global_args
+    global_args = args
+    return args
+
+
+class NetworkHandle(nn.Module):
+    """What ``create_nerf`` returns as ``network_fn``: exposes ``.module`` like the reference's
+    DataParallel/DDP wrapper (run_nerf_batch.py:344-350) without replicating anything."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, sp_input, tp_input, pts, viewdirs=None):
+        outs = []
+        for b in range(pts.shape[0]):
+            outs.append(self.module(_select(sp_input, b), _select(tp_input, b), pts[b], None))
+        return torch.cat(outs, 0)
+
+
+def _net_of(network_fn):
+    return network_fn.module if hasattr(network_fn, "module") else network_fn
+
+
+def _select(d, b):
+    """Subject ``b`` of a batched input dict, batch dim dropped, nothing mutated."""
+    out = {}
+    for k, v in d.items():
+        if torch.is_tensor(v):
+            out[k] = v[b].float() if v.dim() > 0 else v
+        elif isinstance(v, dict):
+            out[k] = _select(v, b)
+        else:
+            out[k] = v
+    return out
+
+
+def run_network(inputs, viewdirs, fn, sp_input=None, tp_input=None):
+    """ref :42-82.  inputs (B,C,S,3) -> (outputs (B,C,S,17), other_loss (1,4))."""
+    flat = torch.reshape(inputs, [inputs.shape[0], -1, inputs.shape[-1]])
+    out = fn(sp_input, tp_input, flat, None)
+    out = torch.reshape(out, list(inputs.shape[:-1]) + [out.shape[-1]])
+    net = _net_of(fn)
+    if net.training and global_args.smooth_loss and torch.is_grad_enabled():
+        raise NotImplementedError("smooth-loss second pass needs the (unbuilt) double-backward path")
+    return out, torch.zeros(1, 4, device=inputs.device)
+
+
+def raw2outputs(raw, z_vals, rays_d, white_bkgd=False):
+    """ref :369-398 -> (rgb_map, disp_map, acc_map, weights, depth_map, T_s); raw (B,C,S,4)."""
+    lib = _lib.load()
+    B, C, S = z_vals.shape
+    dev = raw.device
+    rays8 = torch.zeros(B * C, 8, device=dev)
+    rays8[:, 3:6] = rays_d.reshape(-1, 3)
+    rawc = raw.reshape(-1, 4).float().contiguous()
+    z = z_vals.reshape(-1, S).float().contiguous()
+    rgb, disp, acc, depth = (torch.empty(B * C, 3, device=dev), torch.empty(B * C, device=dev),
+                             torch.empty(B * C, device=dev), torch.empty(B * C, device=dev))
+    w, ts = torch.empty(B * C, S, device=dev), torch.empty(B * C, S, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.mpsnerf_composite(_lib.ptr(rawc), _lib.ptr(rays8), B * C, S, None, None, _lib.ptr(z),
+                                     1 if global_args.occupancy else 0, _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc),
+                                     _lib.ptr(depth), _lib.ptr(w), _lib.ptr(ts), st), "composite")
+    _lib.count_launches(1)
+    rgb, acc = rgb.reshape(B, C, 3), acc.reshape(B, C)
+    if white_bkgd:
+        rgb = rgb + (1.0 - acc[..., None])
+    return rgb, disp.reshape(B, C), acc, w.reshape(B, C, S), depth.reshape(B, C), ts.reshape(B, C, S)
+
+
+def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, perturb=0.0, N_importance=0,
+                network_fine=None, white_bkgd=False, sp_input=None, tp_input=None, perturb_u=None):
+    """ref :401-444.  ray_batch (B,C,8|11) = [o, d, near, far(, viewdirs)] -> dict of outputs.
+
+    ``perturb_u`` (B,C,S) optionally supplies the stratified-sampling uniforms (otherwise drawn
+    with torch.rand on the device, as the reference draws them from the global RNG).
+    """
+    net = _net_of(network_fn)
+    if net.training and torch.is_grad_enabled():
+        raise NotImplementedError("training through the CUDA hot path is not built yet")
+    B, C = ray_batch.shape[:2]
+    dev = ray_batch.device
+    S = int(N_samples)
+    t_vals = torch.linspace(0.0, 1.0, steps=S, device=dev)
+    u = None
+    if perturb > 0.0:
+        u = (perturb_u if perturb_u is not None else torch.rand(B, C, S, device=dev)).float().contiguous()
+    eng = net.engine()
+    net.invalidate_frame_cache()      # like the reference, every render_rays call re-derives the per-frame state
+    per = []
+    for b in range(B):
+        sp, tp = _select(sp_input, b), _select(tp_input, b)
+        ctx = net.frame_context(sp, tp)
+        rays8 = ray_batch[b, :, :8].float().contiguous()
+        per.append(eng.run(ctx, rays8=rays8, S=S, t_vals=t_vals, u=None if u is None else u[b],
+                           occupancy=bool(global_args.occupancy)))
+
+    def stack(key, *shape):
+        return torch.stack([r[key].reshape(C, *shape) for r in per], 0)
+
+    rgb = stack("rgb_map", 3)
+    acc = stack("acc_map")
+    if white_bkgd:
+        rgb = rgb + (1.0 - acc[..., None])
+    zeros3 = torch.zeros(1, 1, 1, 1, device=dev).expand(B, C, S, 3)
+    return {
+        "rgb_map": rgb, "disp_map": stack("disp_map"), "acc_map": acc,
+        "smpl_query_pts": stack("smpl_query_pts", S, 3), "smpl_src_pts": stack("smpl_src_pts", S, 3),
+        "correction_": zeros3, "other_loss": torch.zeros(1, 4, device=dev), "correction": zeros3,
+        "pts_mask": stack("pts_mask", S, 1), "raw": stack("raw", S, 4),
+    }
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, sp_input=None, tp_input=None, **kwargs):
+    """ref :85-97: render in chunks of ``chunk`` rays and concatenate along the ray dim."""
+    all_ret = {}
+    for i in range(0, rays_flat.shape[1], chunk):
+        ret = render_rays(rays_flat[:, i:i + chunk], sp_input=sp_input, tp_input=tp_input, **kwargs)
+        for k, v in ret.items():
+            all_ret.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 1) for k, v in all_ret.items()}
+
+
+def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.0, far=1.0,
+           sp_input=None, tp_input=None, use_viewdirs=False, **kwargs):
+    """ref :100-135.  rays (B,2,N,3), near/far (B,N,1) -> [rgb_map, disp_map, acc_map, extras].
+
+    The whole ray set goes through the kernels at once (they chunk internally by active
+    points); ``chunk`` only determines the width of ``extras['other_loss']`` (4 per chunk).
+    """
+    rays_o, rays_d = rays[:, 0, ...], rays[:, 1, ...]
+    sh = rays_d.shape
+    B = sh[0]
+    rays_o = torch.reshape(rays_o, [B, -1, 3]).float()
+    rays_d = torch.reshape(rays_d, [B, -1, 3]).float()
+    near = torch.reshape(near, [B, -1, 1]).float()
+    far = torch.reshape(far, [B, -1, 1]).float()
+    packed = torch.cat([rays_o, rays_d, near, far], -1)
+    n = packed.shape[1]
+    ret = render_rays(packed, sp_input=sp_input, tp_input=tp_input, **kwargs)
+    nchunks = max(1, (n + chunk - 1) // chunk)
+    ret["other_loss"] = torch.zeros(1, 4 * nchunks, device=packed.device)
+    for k in ("rgb_map", "disp_map", "acc_map", "pts_mask", "raw"):
+        ret[k] = torch.reshape(ret[k], list(sh[:-1]) + list(ret[k].shape[2:]))
+    keys = ("rgb_map", "disp_map", "acc_map")
+    return [ret[k] for k in keys] + [{k: v for k, v in ret.items() if k not in keys}]
+
+
+def create_nerf(args, device=None):
+    """ref :301-366 -> (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer)."""
+    configure(args)
+    device = device or torch.device("cuda")
+    model = return_model(args)
+    grad_vars = list(model.parameters())
+    network_query_fn = lambda inputs, viewdirs, network_fn, sp_input=None, tp_input=None: run_network(
+        inputs, viewdirs, network_fn, sp_input=sp_input, tp_input=tp_input)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    start = 0
+    ckpt_dir = os.path.join(args.basedir, args.expname or "")
+    if args.ft_path is not None and args.ft_path != "None":
+        ckpts = [os.path.join(ckpt_dir, args.ft_path)]
+    elif os.path.isdir(ckpt_dir):
+        ckpts = [os.path.join(ckpt_dir, f) for f in sorted(os.listdir(ckpt_dir)) if ".tar" in f]
+    else:
+        ckpts = []
+    if ckpts and not args.no_reload:
+        ckpt = torch.load(ckpts[-1], map_location="cpu")
+        start = ckpt["global_step"]
+        model.load_state_dict(ckpt["network_fn_state_dict"])
+    model = NetworkHandle(model).to(device)
+    render_kwargs_train = {
+        "network_query_fn": network_query_fn, "perturb": args.perturb, "N_samples": args.N_samples,
+        "network_fn": model, "use_viewdirs": args.use_viewdirs, "N_importance": args.N_importance,
+    }
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test["perturb"] = False
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer

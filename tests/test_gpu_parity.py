@@ -1,0 +1,307 @@
+"""GPU parity tests: CUDA hot path (through the C ABI / public API) vs the CPU oracle and the
+reference-generated golden vectors.  Tolerances follow BASELINE.json's north_star:
+integer outputs (mask, vertex indices) bit-exact; fp32 option rgb <= 1e-4; bf16 rgb <= 1e-2
+and PSNR >= 45 dB."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda_dict(d):
+    return {k: (v.cuda() if torch.is_tensor(v) else _cuda_dict(v) if isinstance(v, dict) else v) for k, v in d.items()}
+
+
+def make_net(scene, sd, precision):
+    from mpsnerf_b200.lib import skinnning_batch as SB
+    SB.set_default_smpl_models(scene.smpl)
+    torch.manual_seed(0)
+    net = SB.SKinningBatch(human_sample=1, use_f2d=1, use_trans=1, smooth_loss=1, num_instances=25, mean_shape=0,
+                           correction_field=0, skinning_field=0, data_set_type="THuman_B", append_rgb=1,
+                           with_viewdirs=0, precision=precision)
+    net.load_state_dict(sd, strict=False)
+    return net.cuda().eval()
+
+
+def psnr(a, b):
+    mse = float(np.mean((a - b) ** 2))
+    return 99.0 if mse == 0 else -10.0 * np.log10(mse)
+
+
+# ------------------------------------------------------------------------------- building blocks
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (192, 128), (160, 256), (128, 192), (16, 64), (64, 320)])
+def test_umma_selftest(N, K):
+    """tcgen05 tile (smem descriptors, swizzle, TMEM epilogue, bulk-copy weights) vs torch."""
+    from mpsnerf_b200 import _lib
+    from mpsnerf_b200.engine import pack_kmajor_sw128
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, generator=g).bfloat16().cuda()
+    b = torch.randn(N, K, generator=g).bfloat16().cuda()
+    packed = pack_kmajor_sw128(b.float(), n_pad=N, k_pad=K)
+    d = torch.zeros(128, N, device="cuda")
+    _lib.check(lib.mpsnerf_selftest_umma(_lib.ptr(a), _lib.ptr(packed), _lib.ptr(d), N, K, None), "selftest")
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().T
+    np.testing.assert_allclose(d.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+def test_knn1_bit_exact_against_oracle():
+    from mpsnerf_b200 import _lib, synthetic
+    from oracle import oracle as O
+    lib = _lib.load()
+    rng = np.random.RandomState(0)
+    verts = synthetic.load_template("n", "T")
+    q = np.concatenate([
+        verts[rng.randint(0, 6890, 20000)] + rng.normal(0, 0.02, (20000, 3)).astype(np.float32),   # near the surface
+        rng.uniform(-1.5, 1.5, (20000, 3)).astype(np.float32),                                    # anywhere (fallback path)
+        verts[:2000],                                                                              # exactly on vertices
+        np.array([[50.0, -30.0, 10.0], [0.0, 0.0, 0.0]], dtype=np.float32),
+    ]).astype(np.float32)
+    for cell in (0.0505, 0.06, 0.2):
+        gb = lib.mpsnerf_grid_bytes(6890)
+        grid = torch.empty(gb, dtype=torch.uint8, device="cuda")
+        v = torch.from_numpy(verts).cuda()
+        _lib.check(lib.mpsnerf_grid_build(_lib.ptr(v), 6890, None, None, cell, _lib.ptr(grid), gb, None), "grid")
+        qd = torch.from_numpy(q).cuda()
+        d2 = torch.empty(len(q), device="cuda")
+        idx = torch.empty(len(q), dtype=torch.int32, device="cuda")
+        _lib.check(lib.mpsnerf_knn1(_lib.ptr(qd), len(q), _lib.ptr(grid), _lib.ptr(d2), _lib.ptr(idx), None), "knn1")
+        d2o, idxo = O.knn1(q, verts)
+        assert np.array_equal(idx.cpu().numpy().astype(np.int64), idxo)
+        assert np.array_equal(d2.cpu().numpy(), d2o)
+
+
+def test_composite_against_oracle():
+    from mpsnerf_b200 import run_nerf_batch as R
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(3)
+    for S in (1, 7, 64, 128):
+        N = 300
+        raw = torch.randn(1, N, S, 4, generator=g) * 6
+        raw[0, :40] = -80.0                                  # empty rays -> disp NaN
+        raw[0, 40:80, :, 3] = 60.0                           # opaque at the first sample
+        z = torch.sort(torch.rand(1, N, S, generator=g) * 2 + 1, dim=-1).values
+        d = torch.randn(1, N, 3, generator=g)
+        rgb, disp, acc, w, depth, ts = R.raw2outputs(raw.cuda(), z.cuda(), d.cuda())
+        o_rgb, o_disp, o_acc, o_w, o_depth = O.raw2outputs(raw[0], z[0], d[0])
+        np.testing.assert_allclose(rgb[0].cpu().numpy(), o_rgb.numpy(), atol=2e-6)
+        np.testing.assert_allclose(acc[0].cpu().numpy(), o_acc.numpy(), atol=2e-6)
+        np.testing.assert_allclose(w[0].cpu().numpy(), o_w.numpy(), atol=2e-6)
+        np.testing.assert_allclose(depth[0].cpu().numpy(), o_depth.numpy(), atol=1e-5)
+        dn, on = disp[0].cpu().numpy(), o_disp.numpy()
+        assert np.array_equal(np.isnan(dn), np.isnan(on)) and np.isnan(on[:40]).all()
+        ok = ~np.isnan(on) & (o_acc.numpy() > 1e-4)
+        np.testing.assert_allclose(dn[ok], on[ok], rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------- stage parity vs oracle
+def _engine_consts(ctx, oc):
+    """Oracle frame constants with the per-frame matrices replaced by the ones the engine
+    uploaded, so that the bit-exact stages are compared on identical inputs."""
+    fr = ctx.keep[0]
+    c = dict(oc)
+    f32 = lambda a, *s: np.array(list(a), dtype=np.float32).reshape(*s)
+    c.update(A_tp=f32(fr.A_tp, 24, 12), A_big_tp=f32(fr.A_big_tp, 24, 12), A_big_sp=f32(fr.A_big_sp, 24, 12),
+             A_sp=f32(fr.A_sp, 24, 12), R_tp=f32(fr.R_tp, 3, 3), Th_tp=f32(fr.Th_tp, 3),
+             Rinv_sp=f32(fr.Rinv_sp, 3, 3), Th_sp=f32(fr.Th_sp, 3))
+    return c
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stages_against_oracle(case, precision):
+    from mpsnerf_b200.run_nerf_batch import _select
+    from oracle import oracle as O
+    name, scene, sd, g = case
+    net = make_net(scene, sd, precision)
+    ids, S = g["ray_ids"], int(g["S"])
+    sp, tp = _select(_cuda_dict(scene.sp_input), 0), _select(_cuda_dict(scene.tp_input), 0)
+    ctx = net.frame_context(sp, tp)
+    eng = net.engine()
+    eng.debug = {}
+    rays8 = torch.from_numpy(np.concatenate([scene.rays_o[ids], scene.rays_d[ids], scene.near[ids, None],
+                                             scene.far[ids, None]], 1)).cuda()
+    u = torch.from_numpy(g["u"]).cuda() if "u" in g else None
+    t_vals = torch.linspace(0, 1, S, device="cuda")
+    res = eng.run(ctx, rays8=rays8, S=S, t_vals=t_vals, u=u)
+    torch.cuda.synchronize()
+    dbg = {k: (torch.cat(v).cpu().numpy() if isinstance(v, list) else v.cpu().numpy()) for k, v in eng.debug.items()}
+    eng.debug = None
+
+    smpl = O.smpl_tensors(scene.smpl)
+    sp_c, tp_c = O.squeeze_inputs(scene.sp_input, scene.tp_input)
+    oc = O.frame_constants(smpl, sp_c, tp_c)
+    for k in ("A_tp", "A_big_tp", "A_big_sp", "A_sp"):
+        np.testing.assert_allclose(_engine_consts(ctx, oc)[k], oc[k], atol=2e-6)
+    c = _engine_consts(ctx, oc)
+    z = O.sample_z(scene.near[ids], scene.far[ids], S, g.get("u"))
+    pts = O.sample_points(scene.rays_o[ids], scene.rays_d[ids], z).reshape(-1, 3)
+    latent = ctx.latent.permute(0, 3, 1, 2).cpu()          # the oracle consumes the same latent
+    raw17, st = O.forward_points(smpl, sd, sp_c, tp_c, pts, bf16=(precision == "bf16"), latent=latent, consts=c,
+                                 return_stages=True)
+    # ---- integer stages: bit-exact
+    mask = res["pts_mask"].cpu().numpy() > 0.5
+    assert np.array_equal(mask, st["mask"])
+    order = np.argsort(dbg["act_pid"], kind="stable")
+    assert np.array_equal(dbg["act_pid"][order], st["active"])
+    assert np.array_equal(dbg["act_idx2"][order].astype(np.int64), st["idx2"])
+    assert np.array_equal(dbg["act_q"][order], st["q"])
+    assert np.array_equal(dbg["xc"][order], st["xc"])
+    assert np.array_equal(dbg["idx3"][order].astype(np.int64), st["idx3"])
+    assert np.array_equal(dbg["xw"][order], st["xw"])
+    assert np.array_equal(res["smpl_query_pts"].cpu().numpy()[st["active"]], st["q"])
+    assert np.array_equal(res["smpl_src_pts"].cpu().numpy()[st["active"]], st["xs"])
+    assert not res["smpl_src_pts"].cpu().numpy()[~mask].any()
+    # ---- floating-point stages
+    np.testing.assert_allclose(dbg["uv"][order].transpose(1, 0, 2), st["uv"], rtol=1e-5, atol=2e-3)
+    np.testing.assert_allclose(dbg["tokens"][order][..., :155], st["tokens"], atol=2e-4)
+    assert not dbg["tokens"][..., 155:].any()
+    raw = res["raw"].cpu().numpy()
+    assert np.all(raw[~mask] == -80.0)
+    scale = max(1.0, float(np.abs(raw17[mask, :4]).max()))
+    tol = 2e-4 if precision == "fp32" else 2e-2     # bf16: vs the bf16-operand emulation of the oracle
+    np.testing.assert_allclose(raw[mask], raw17[mask, :4], atol=tol * scale)
+    o_rgb, o_disp, o_acc, _, o_depth = O.raw2outputs(torch.from_numpy(raw17[:, :4].reshape(-1, S, 4)),
+                                                     torch.from_numpy(z), torch.from_numpy(scene.rays_d[ids]))
+    np.testing.assert_allclose(res["rgb_map"].cpu().numpy(), o_rgb.numpy(), atol=1e-4 if precision == "fp32" else 5e-3)
+    np.testing.assert_allclose(res["acc_map"].cpu().numpy(), o_acc.numpy(), atol=1e-4 if precision == "fp32" else 5e-3)
+
+
+# ------------------------------------------------------------------------------- public API vs the reference's outputs
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_render_against_reference_golden(case, precision):
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    name, scene, sd, g = case
+    net = R.NetworkHandle(make_net(scene, sd, precision))
+    ids, S = g["ray_ids"], int(g["S"])
+    rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
+    kw = dict(network_fn=net, network_query_fn=None, N_samples=S, perturb=1.0 if "u" in g else False, N_importance=0)
+    if "u" in g:
+        kw["perturb_u"] = torch.from_numpy(g["u"])[None].cuda()
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+    rgb, disp, acc, extras = R.render(chunk=100, rays=rays, near=near, far=far, sp_input=sp, tp_input=tp,
+                                      use_viewdirs=True, **kw)
+    torch.cuda.synchronize()
+    assert rgb.shape == (1, len(ids), 3) and disp.shape == (1, len(ids)) and acc.shape == (1, len(ids))
+    assert extras["raw"].shape == (1, len(ids), S, 4) and extras["pts_mask"].shape == (1, len(ids), S, 1)
+    for k in ("smpl_query_pts", "smpl_src_pts", "correction", "correction_"):
+        assert extras[k].shape == (1, len(ids), S, 3)
+    assert extras["other_loss"].shape == (1, 4 * ((len(ids) + 99) // 100))
+    # the caller's dicts are untouched (the reference mutates them)
+    assert sp["img_all"].dim() == 5 and sp["gender"].shape == (1,)
+    mask = extras["pts_mask"][0, ..., 0].cpu().numpy() > 0.5
+    gmask = g["pts_mask"][..., 0] > 0
+    flips = mask != gmask                      # q via torch.mm in the reference vs pinned ops here
+    assert flips.sum() <= 2
+    good = ~flips.any(1)
+    both = mask & gmask
+    raw = extras["raw"][0].cpu().numpy()
+    scale = max(1.0, float(np.abs(g["raw"][gmask]).max()))
+    np.testing.assert_allclose(extras["smpl_query_pts"][0].cpu().numpy()[both], g["smpl_query_pts"][both], atol=2e-6)
+    close = np.isclose(extras["smpl_src_pts"][0].cpu().numpy()[both], g["smpl_src_pts"][both], atol=1e-4).all(-1)
+    assert close.mean() > 0.995            # the rest are nearest-vertex near-ties resolved differently by torch.mm/LU
+    sel = both.copy()
+    sel[both] = close
+    np.testing.assert_allclose(raw[sel], g["raw"][sel], atol=(5e-4 if precision == "fp32" else 3e-2) * scale)
+    assert np.all(raw[~mask] == -80.0)
+    ray_ok = good & ~(both & ~sel).any(1)
+    d_rgb = np.abs(rgb[0].cpu().numpy()[ray_ok] - g["rgb_map"][ray_ok])
+    d_acc = np.abs(acc[0].cpu().numpy()[ray_ok] - g["acc_map"][ray_ok])
+    if precision == "fp32":
+        assert d_rgb.max() <= 1e-4 and d_acc.max() <= 1e-4, (d_rgb.max(), d_acc.max())
+    else:
+        assert d_rgb.max() <= 1e-2, d_rgb.max()
+        assert psnr(rgb[0].cpu().numpy()[ray_ok], g["rgb_map"][ray_ok]) >= 45.0
+    dn, gn = disp[0].cpu().numpy()[ray_ok], g["disp_map"][ray_ok]
+    assert np.array_equal(np.isnan(dn), np.isnan(gn))
+
+
+# ------------------------------------------------------------------------------- edge cases and full-size properties
+def test_edge_cases():
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    scene, sd, g = load_case("plain")
+    net = R.NetworkHandle(make_net(scene, sd, "fp32"))
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+    kw = dict(network_fn=net, N_samples=64, perturb=False, sp_input=sp, tp_input=tp, use_viewdirs=True)
+    # rays that miss the body entirely: everything masked, acc = 0, disp = NaN
+    rays, near, far = synthetic.rays_tensor(scene, np.arange(0, 700), device="cuda")   # top image rows, above the head
+    rays[:, 1] = -rays[:, 1]                                                              # look away
+    rgb, disp, acc, ex = R.render(rays=rays, near=near, far=far, **kw)
+    assert float(ex["pts_mask"].sum()) == 0 and float(acc.abs().max()) == 0 and bool(torch.isnan(disp).all())
+    assert bool((ex["raw"] == -80).all())
+    # empty ray set
+    rgb, disp, acc, ex = R.render(rays=rays[:, :, :0], near=near[:, :0], far=far[:, :0], **kw)
+    assert rgb.shape == (1, 0, 3) and ex["raw"].shape == (1, 0, 64, 4)
+    # ragged sizes: a ray count that is not a multiple of any tile, S = 1 and S = 37
+    ids = synthetic.inbox_ray_subset(scene, 333)
+    rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
+    ref = R.render(rays=rays, near=near, far=far, **kw)
+    for S in (1, 37):
+        kw2 = dict(kw, N_samples=S)
+        out = R.render(rays=rays, near=near, far=far, **kw2)
+        assert out[3]["raw"].shape == (1, 333, S, 4)
+    # chunk invariance: a sub-range rendered alone equals the same rays inside the larger call, bit for bit
+    sub = R.render(rays=rays[:, :, 100:200], near=near[:, 100:200], far=far[:, 100:200], **kw)
+    assert torch.equal(sub[0], ref[0][:, 100:200]) and torch.equal(sub[3]["raw"], ref[3]["raw"][:, 100:200])
+
+
+def test_network_fn_direct_and_extract_mesh():
+    """network_fn(sp, tp, pts, dirs) contract (lib/skinnning_batch.py:333-514) and the
+    extract_mesh mode used by the density-grid query (extract_thuman_mesh.py:114-125)."""
+    from oracle import oracle as O
+    scene, sd, g = load_case("plain")
+    net = make_net(scene, sd, "fp32")
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+    v = scene.tp_input["vertices"][0].numpy()
+    rng = np.random.RandomState(5)
+    pts = (v[rng.randint(0, 6890, 3000)] + rng.normal(0, 0.03, (3000, 3))).astype(np.float32)
+    out = net(sp, tp, torch.from_numpy(pts)[None].cuda(), None)
+    assert out.shape == (1, 3000, 17)
+    smpl = O.smpl_tensors(scene.smpl)
+    sp_c, tp_c = O.squeeze_inputs(scene.sp_input, scene.tp_input)
+    ref = O.forward_points(smpl, sd, sp_c, tp_c, pts)
+    o = out[0].cpu().numpy()
+    assert np.array_equal(o[:, 4], ref[:, 4])
+    np.testing.assert_allclose(o[:, :4], ref[:, :4], atol=5e-4)
+    np.testing.assert_allclose(o[:, 11:], ref[:, 11:], atol=1e-4)
+    assert not o[:, 5:11].any()
+    net.set_extract_mesh(True)
+    tv = scene.sp_input["t_vertices"][0].numpy()
+    cpts = (tv[rng.randint(0, 6890, 2000)] + rng.normal(0, 0.02, (2000, 3))).astype(np.float32)
+    out = net(sp, tp, torch.from_numpy(cpts)[None].cuda(), None)
+    assert out.shape == (1, 2000, 4)
+    ref = O.forward_points(smpl, sd, sp_c, tp_c, cpts, extract_mesh=True)
+    np.testing.assert_allclose(out[0].cpu().numpy(), ref, atol=5e-4)
+
+
+@pytest.mark.parametrize("precision", ["bf16"])
+def test_full_frame_properties(precision):
+    """BASELINE config 2 size (512x512 rays x 64 samples): determinism, sub-range invariance and
+    an oracle spot check on rays drawn from the full-frame result."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    from oracle import oracle as O
+    scene, sd, g = load_case("plain")
+    net = R.NetworkHandle(make_net(scene, sd, precision))
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+    rays, near, far = synthetic.rays_tensor(scene, None, device="cuda")
+    kw = dict(network_fn=net, N_samples=64, perturb=False, sp_input=sp, tp_input=tp, use_viewdirs=True)
+    a = R.render(rays=rays, near=near, far=far, **kw)
+    b = R.render(rays=rays, near=near, far=far, **kw)
+    assert a[0].shape == (1, 512 * 512, 3)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3]["raw"], b[3]["raw"]) and torch.equal(a[3]["pts_mask"], b[3]["pts_mask"])
+    n_act = int(a[3]["pts_mask"].sum())
+    assert 0.02 < n_act / (512 * 512 * 64) < 0.2
+    assert bool((a[3]["raw"][a[3]["pts_mask"][..., 0] == 0] == -80).all())
+    ids = np.random.RandomState(1).choice(512 * 512, 1024, replace=False)
+    ids.sort()
+    r = O.render(O.smpl_tensors(scene.smpl), sd, scene.sp_input, scene.tp_input, scene.rays_o[ids], scene.rays_d[ids],
+                 scene.near[ids], scene.far[ids], S=64, bf16=(precision == "bf16"))
+    m = a[3]["pts_mask"][0, ids, :, 0].cpu().numpy() > 0.5
+    assert (m != (r["pts_mask"][..., 0] > 0.5)).sum() <= 2       # encoder on GPU vs CPU does not touch the mask
+    d = np.abs(a[0][0, ids].cpu().numpy() - r["rgb_map"])
+    assert d.max() <= 1e-2 and psnr(a[0][0, ids].cpu().numpy(), r["rgb_map"]) >= 45.0

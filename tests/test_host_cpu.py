@@ -1,0 +1,108 @@
+"""CPU-side checks: config parsing, state-dict surface, weight packing, C-ABI symbols."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_config_files_parse_like_reference():
+    from mpsnerf_b200.parser_config import config_parser
+    a = config_parser().parse_args(["--config", os.path.join(ROOT, "configs", "canonical_transformer.txt")])
+    assert a.model == "skinning_batch" and a.use_trans == 1 and a.append_rgb == 1 and a.N_samples == 128
+    assert a.chunk == 12000 and a.use_viewdirs is True and a.white_bkgd is False and a.human_sample == 1
+    assert a.correction_field == 0 and a.skinning_field == 0 and a.mean_shape == 0 and a.num_instance == 25
+    # CLI wins over the file
+    b = config_parser().parse_args(["--config", os.path.join(ROOT, "configs", "canonical_transformer.txt"), "--N_samples", "64"])
+    assert b.N_samples == 64
+    # h36m.txt uses the abbreviation i_test -> --i_testset (parser_config.py:101)
+    h = config_parser().parse_args(["--config", os.path.join(ROOT, "configs", "h36m.txt")])
+    assert h.i_testset == 6000 and h.data_set_type == "H36M_P" and h.num_instance == 6
+
+
+def _make_net():
+    from mpsnerf_b200 import synthetic
+    from mpsnerf_b200.lib import skinnning_batch as SB
+    from mpsnerf_b200.parser_config import config_parser
+    from mpsnerf_b200.model_selection import return_model
+    SB.set_default_smpl_models(synthetic.make_smpl("n", 0))
+    args = config_parser().parse_args(["--config", os.path.join(ROOT, "configs", "canonical_transformer.txt")])
+    return return_model(args)
+
+
+def test_state_dict_surface():
+    net = _make_net()
+    sd = net.state_dict()
+    shapes = {
+        "pts_linears.0.weight": (256, 194), "pts_linears.5.weight": (256, 450), "pts_linears.7.bias": (256,),
+        "alpha_linear.weight": (1, 256), "feature_linear.weight": (256, 256), "views_linear.weight": (128, 411),
+        "rgb_linear.weight": (3, 128), "transformer.layers.0.0.fn.norm.weight": (155,),
+        "transformer.layers.1.0.fn.fn.to_qkv.weight": (768, 155),
+        "transformer.layers.0.0.fn.fn.to_out.0.weight": (155, 256), "transformer.layers.0.0.fn.fn.to_out.0.bias": (155,),
+        "transformer.layers.1.1.fn.fn.net.0.weight": (128, 155), "transformer.layers.1.1.fn.fn.net.3.weight": (155, 128),
+        "latent_codes.weight": (25, 128), "pos_enc._freqs": (1, 12, 1), "view_enc._freqs": (1, 8, 1),
+        "encoder_2d.model.conv1.weight": (64, 3, 7, 7), "encoder_2d.model.layer4.2.bn2.running_var": (512,),
+        "encoder_3d.conv0.0.weight": (16, 3, 3, 3, 3), "encoder_3d.down3.1.running_mean": (128,),
+        "forward_deform.output_linear.weight": (3, 256), "backward_deform.pts_time_linears.3.weight": (256, 256),
+    }
+    for k, s in shapes.items():
+        assert k in sd, k
+        assert tuple(sd[k].shape) == s, (k, tuple(sd[k].shape))
+    assert "transformer.layers.0.0.fn.fn.to_qkv.bias" not in sd
+    from mpsnerf_b200 import synthetic
+    missing = net.load_state_dict(synthetic.seeded_state_dict(0), strict=False)
+    assert not missing.unexpected_keys
+
+
+def test_unsupported_configs_fail_loudly():
+    net = _make_net()
+    net.mean_shape = 1
+    with pytest.raises(NotImplementedError):
+        net._check_supported()
+    from mpsnerf_b200.model_selection import return_model
+    from mpsnerf_b200.parser_config import config_parser
+    with pytest.raises(NotImplementedError):
+        return_model(config_parser().parse_args(["--model", "direct_deform"]))
+
+
+def test_no_cpu_path():
+    from mpsnerf_b200 import synthetic
+    net = _make_net().eval()
+    sc = synthetic.make_scene("thuman", seed=0, H=64, W=64)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        net(sc.sp_input, sc.tp_input, torch.zeros(1, 8, 3), None)
+
+
+def test_pack_kmajor_sw128_matches_address_formula():
+    from mpsnerf_b200.engine import pack_kmajor_sw128
+    g = torch.Generator().manual_seed(1)
+    for N, K in ((256, 194), (768, 155), (16, 64), (160, 256)):
+        w = torch.randn(N, K, generator=g)
+        blob = pack_kmajor_sw128(w).numpy().view(np.uint16)
+        n_pad, k_pad = (N + 15) // 16 * 16, (K + 63) // 64 * 64
+        wp = torch.zeros(n_pad, k_pad, dtype=torch.bfloat16)
+        wp[:N, :K] = w.bfloat16()
+        ref = wp.view(torch.int16).numpy().view(np.uint16)
+        rng = np.random.RandomState(0)
+        for _ in range(500):
+            r, k = rng.randint(n_pad), rng.randint(k_pad)
+            chunk, j16, e = k // 64, (k % 64) // 8, k % 8
+            byte = chunk * n_pad * 128 + (r // 8) * 1024 + (r % 8) * 128 + ((j16 ^ (r % 8)) << 4) + 2 * e
+            assert blob[byte // 2] == ref[r, k]
+
+
+def test_cabi_exports_every_declared_symbol():
+    from mpsnerf_b200 import _lib, build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(ROOT, "include", "mpsnerf.h")).read()
+    declared = set(re.findall(r"\b(mpsnerf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mpsnerf_abi_version() == 1
+    assert ctypes.sizeof(_lib.Frame) == 4 * (3 + 9 + 9 + 3 + 4 * 288 + 72 + 24 + 72 + 8)
