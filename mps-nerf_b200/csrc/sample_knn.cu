@@ -24,7 +24,7 @@ sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const
   const GridView g = grid_view(grid_buf);
   __shared__ GridHdr s_hdr;
   __shared__ float s_fr[12];                 // Th(3) R(9)
-  __shared__ float s_q[kK1Threads * 3];
+  __shared__ __align__(16) float s_q[kK1Threads * 3];   // read back as float4 in phase 3
   __shared__ float s_d2[kK1Threads];
   __shared__ int s_idx[kK1Threads];
   __shared__ int s_cand[kK1Threads];

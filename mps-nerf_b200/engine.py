@@ -168,7 +168,9 @@ class RenderEngine:
         ctx = FrameContext()
         ctx.n_views = V
         # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
-        latent = self.net.encoder_2d(sp["img_all"])
+        # (cuDNN convolutions default to TF32; the fp32 precision mode keeps true fp32 end to end)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=(self.precision != "fp32")):
+            latent = self.net.encoder_2d(sp["img_all"])
         fr.feat_w, fr.feat_h = latent.shape[-1], latent.shape[-2]
         ctx.latent = latent.permute(0, 2, 3, 1).contiguous().float()
         ctx.img4 = F.pad(sp["img_all"].permute(0, 2, 3, 1), (0, 1)).contiguous().float()
@@ -211,6 +213,10 @@ class RenderEngine:
         ss = torch.empty(P, 3, device=dev)
         out = {"raw": raw, "pts_mask": mask, "smpl_query_pts": sq, "smpl_src_pts": ss}
         if P == 0:
+            if composite and points is None:
+                out.update(rgb_map=torch.empty(N, 3, device=dev), disp_map=torch.empty(N, device=dev),
+                           acc_map=torch.empty(N, device=dev), depth_map=torch.empty(N, device=dev))
+            out["n_active"] = 0
             return out
         act_pid = self._buf("act_pid", 4 * P, dev).view(torch.int32)
         act_idx2 = self._buf("act_idx2", 4 * P, dev).view(torch.int32)

@@ -25,9 +25,15 @@ class SpatialEncoder(nn.Module):
         self.use_first_pool = use_first_pool
         weights = None
         if pretrained:
-            try:  # ImageNet weights when they are cached locally; random init offline
-                weights = torchvision.models.get_model_weights(backbone).DEFAULT
-                self.model = torchvision.models.get_model(backbone, weights=weights)
+            # ImageNet weights only when they are already cached locally (no download attempt
+            # offline); otherwise random init -- checkpoints overwrite them anyway
+            import os
+            try:
+                w = torchvision.models.get_model_weights(backbone).DEFAULT
+                cached = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
+                if os.path.exists(cached):
+                    self.model = torchvision.models.get_model(backbone, weights=w)
+                    weights = w
             except Exception:
                 weights = None
         if weights is None:

@@ -1,0 +1,97 @@
+"""Pack the live weights into the blob consumed by the tcgen05 kernels (csrc/dense_tc.cu).
+
+Layout (bytes; every weight tile is K-major bf16 in SWIZZLE_128B chunks, see
+``engine.pack_kmajor_sw128``), in the exact order the kernels stream it:
+
+  transformer, per layer l (466 944 B):
+      qkv_0[3 chunks x 192 rows]; then for h = 1..3: Wo_{h-1}[1 x 160], qkv_h[3 x 192];
+      Wo_3[1 x 160]; W1[3 x 128]; W2[2 x 160]
+      qkv_h rows = (q_h | k_h | v_h) = to_qkv rows 64h.., 256+64h.., 512+64h..   (K = 155 -> 192)
+  MLP (1 425 408 B):
+      L0[4 x 256] (K order: tok0 155, 5 zero, PE 39, zero to 256); L1..L4[4 x 256] each;
+      L5[x part 4 x 256 | h part 4 x 256]; L6, L7[4 x 256]; feature[4 x 256];
+      views[tok1 part 3 x 128 | feature part 4 x 128]
+  fp32 section:
+      per transformer layer 1088 floats: ln1_g, ln1_b, pend_in, ln2_g, ln2_b, pend_mid (160 each), b1 (128)
+      then pend_out (160): the biases of to_out / net.3 are *deferred*: the residual stream in
+      TMEM never contains them, every reader adds the running sum (pend_*) instead;
+      MLP: b0..b7 (8 x 256), w_alpha (256), b_feature (256), b_views (128), w_rgb (3 x 128),
+      b_alpha, b_rgb (3).
+"""
+import torch
+
+from .engine import pack_kmajor_sw128
+
+T_LAYER_BYTES = 12 * 24576 + 4 * 20480 + 3 * 16384 + 2 * 20480
+T_BYTES = 2 * T_LAYER_BYTES
+M_BYTES = 40 * 32768 + 7 * 16384
+T_FLOATS = 2 * 1088 + 160
+M_FLOATS = 8 * 256 + 256 + 256 + 128 + 384 + 4
+FLOAT_OFFSET = T_BYTES + M_BYTES
+BLOB_BYTES = FLOAT_OFFSET + 4 * (T_FLOATS + M_FLOATS)
+
+
+def _pad160(v):
+    out = torch.zeros(160, dtype=torch.float32, device=v.device)
+    out[:v.numel()] = v.float()
+    return out
+
+
+@torch.no_grad()
+def pack_weights_bf16(net, device=None):
+    sd = {k: v.detach().float() for k, v in net.state_dict().items()}
+    dev = device or sd["alpha_linear.weight"].device
+    sd = {k: v.to(dev) for k, v in sd.items() if k.startswith(("transformer.", "pts_linears.", "alpha_linear.",
+                                                               "feature_linear.", "views_linear.", "rgb_linear."))}
+    parts, floats = [], []
+    pend = torch.zeros(160, device=dev)
+    for l in range(2):
+        p = f"transformer.layers.{l}."
+        wqkv, wo = sd[p + "0.fn.fn.to_qkv.weight"], sd[p + "0.fn.fn.to_out.0.weight"]
+        w1, w2 = sd[p + "1.fn.fn.net.0.weight"], sd[p + "1.fn.fn.net.3.weight"]
+        qkv = [torch.cat([wqkv[64 * h:64 * h + 64], wqkv[256 + 64 * h:256 + 64 * h + 64],
+                          wqkv[512 + 64 * h:512 + 64 * h + 64]], 0) for h in range(4)]
+        out = [wo[:, 64 * h:64 * h + 64] for h in range(4)]
+        parts.append(pack_kmajor_sw128(qkv[0], 192, 192))
+        for h in range(1, 4):
+            parts.append(pack_kmajor_sw128(out[h - 1], 160, 64))
+            parts.append(pack_kmajor_sw128(qkv[h], 192, 192))
+        parts.append(pack_kmajor_sw128(out[3], 160, 64))
+        parts.append(pack_kmajor_sw128(w1, 128, 192))
+        parts.append(pack_kmajor_sw128(w2, 160, 128))
+        pend_in = pend.clone()
+        pend_mid = pend_in + _pad160(sd[p + "0.fn.fn.to_out.0.bias"])
+        pend = pend_mid + _pad160(sd[p + "1.fn.fn.net.3.bias"])
+        floats += [_pad160(sd[p + "0.fn.norm.weight"]), _pad160(sd[p + "0.fn.norm.bias"]), pend_in,
+                   _pad160(sd[p + "1.fn.norm.weight"]), _pad160(sd[p + "1.fn.norm.bias"]), pend_mid,
+                   sd[p + "1.fn.fn.net.0.bias"]]
+    floats.append(pend)
+    assert sum(x.numel() for x in parts) == T_BYTES
+
+    def perm_x(w):      # columns [PE 39 | tok0 155] -> [tok0 155, 5 zeros, PE 39]
+        o = torch.zeros(w.shape[0], 199, device=dev)
+        o[:, :155] = w[:, 39:194]
+        o[:, 160:199] = w[:, :39]
+        return o
+
+    W = [sd[f"pts_linears.{i}.weight"] for i in range(8)]
+    parts.append(pack_kmajor_sw128(perm_x(W[0]), 256, 256))
+    for i in range(1, 5):
+        parts.append(pack_kmajor_sw128(W[i], 256, 256))
+    parts.append(pack_kmajor_sw128(perm_x(W[5][:, :194]), 256, 256))
+    parts.append(pack_kmajor_sw128(W[5][:, 194:], 256, 256))
+    parts.append(pack_kmajor_sw128(W[6], 256, 256))
+    parts.append(pack_kmajor_sw128(W[7], 256, 256))
+    parts.append(pack_kmajor_sw128(sd["feature_linear.weight"], 256, 256))
+    wv = sd["views_linear.weight"]
+    parts.append(pack_kmajor_sw128(wv[:, 256:411], 128, 192))
+    parts.append(pack_kmajor_sw128(wv[:, :256], 128, 256))
+    assert sum(x.numel() for x in parts) == T_BYTES + M_BYTES
+    floats += [sd[f"pts_linears.{i}.bias"] for i in range(8)]
+    floats += [sd["alpha_linear.weight"].reshape(-1), sd["feature_linear.bias"], sd["views_linear.bias"],
+               sd["rgb_linear.weight"].reshape(-1), sd["alpha_linear.bias"].reshape(-1), sd["rgb_linear.bias"].reshape(-1)]
+    f = torch.cat([x.reshape(-1).float() for x in floats])
+    assert f.numel() == T_FLOATS + M_FLOATS, f.numel()
+    blob = torch.cat(parts + [f.contiguous().view(torch.uint8)])
+    assert blob.numel() == BLOB_BYTES
+    return blob.contiguous()
