@@ -217,8 +217,16 @@ def test_render_against_reference_golden(case, precision):
     else:
         assert d_rgb.max() <= 1e-2, d_rgb.max()
         assert psnr(rgb[0].cpu().numpy()[ray_ok], g["rgb_map"][ray_ok]) >= 45.0
+    # disp = 1/max(1e-10, depth/acc) is NaN exactly when acc == 0.  Rays without active samples must
+    # be NaN on both sides; rays whose acc is a few ulp from 0 (1 - exp(-tiny), GPU expf vs CPU exp)
+    # are degenerate and excluded from the pattern check.
     dn, gn = disp[0].cpu().numpy()[ray_ok], g["disp_map"][ray_ok]
-    assert np.array_equal(np.isnan(dn), np.isnan(gn))
+    a_m, a_g = acc[0].cpu().numpy()[ray_ok], g["acc_map"][ray_ok]
+    empty = ~gmask[ray_ok].any(1)
+    assert np.isnan(dn[empty]).all() and np.isnan(gn[empty]).all()
+    solid = np.minimum(a_m, a_g) > 1e-5
+    assert not np.isnan(dn[solid]).any() and not np.isnan(gn[solid]).any()
+    np.testing.assert_allclose(dn[solid], gn[solid], rtol=2e-2 if precision == "bf16" else 2e-3)
 
 
 # ------------------------------------------------------------------------------- edge cases and full-size properties
