@@ -100,11 +100,16 @@ __device__ __forceinline__ void ln_to_operand(float (&x)[160], const float* __re
                                               const float* __restrict__ g, const float* __restrict__ b,
                                               uint8_t* YA, int r) {
   float s = 0.f;
+  if (pend) {
+    const float4* p4 = reinterpret_cast<const float4*>(pend);
 #pragma unroll
-  for (int c = 0; c < 160; ++c) {
-    if (pend) x[c] += pend[c];
-    if (c < 155) s += x[c];
+    for (int c = 0; c < 40; ++c) {
+      const float4 t = p4[c];
+      x[4 * c] += t.x; x[4 * c + 1] += t.y; x[4 * c + 2] += t.z; x[4 * c + 3] += t.w;
+    }
   }
+#pragma unroll
+  for (int c = 0; c < 155; ++c) s += x[c];
   const float mean = s * (1.0f / 155.0f);
   float v = 0.f;
 #pragma unroll
@@ -113,8 +118,12 @@ __device__ __forceinline__ void ln_to_operand(float (&x)[160], const float* __re
 #pragma unroll
   for (int c0 = 0; c0 < 160; c0 += 8) {
     float y[8];
+    const float4 g0 = *reinterpret_cast<const float4*>(g + c0), g1 = *reinterpret_cast<const float4*>(g + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(b + c0), b1 = *reinterpret_cast<const float4*>(b + c0 + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = fmaf((x[c0 + i] - mean) * rstd, g[c0 + i], b[c0 + i]);
+    for (int i = 0; i < 8; ++i) y[i] = fmaf((x[c0 + i] - mean) * rstd, gg[i], bb[i]);
     store_a8(YA, 128, r, c0, pack8_bf16(y));
   }
 }
@@ -130,13 +139,14 @@ __device__ __forceinline__ void load_x160(uint32_t taddr, float (&x)[160]) {
   }
 }
 
+template <int kV>
 __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Pipe* pipe = reinterpret_cast<Pipe*>(smem + kT_PIPE);
   float* FP = reinterpret_cast<float*>(smem + kT_FP);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int V = a.V;
-  const int ppt = 128 / V;
+  constexpr int V = kV;
+  constexpr int ppt = 128 / V;
   const int64_t ntiles = (a.count + ppt - 1) / ppt;
 
   if (tid == 0) {
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
     uint32_t g = 0;
     auto hand_over = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(&pipe->a_bar); };
     auto wait_d = [&]() { mbar_wait(&pipe->d_bar, g & 1); ++g; tc_fence_after(); };
-    const int rows = ppt * V;
+    constexpr int rows = ppt * V;
     const int p0 = (r < rows) ? (r / V) * V : 0;      // first row of this row's point (attention partners)
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -310,8 +320,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
 #pragma unroll
             for (int i = 0; i < 32; ++i) q[32 + i] = t[i];
           }
-          float dots[MPSNERF_MAX_VIEWS];
+          float dots[V];
           float mx = -1e30f;
+#pragma unroll
           for (int j = 0; j < V; ++j) {
             const int rj = p0 + j;
             const uint8_t* src = KX + rj * 128;
@@ -331,11 +342,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
             mx = fmaxf(mx, dots[j]);
           }
           float den = 0.f;
+#pragma unroll
           for (int j = 0; j < V; ++j) { dots[j] = __expf(dots[j] - mx); den += dots[j]; }
           const float inv = 1.0f / den;
           float o[64];
 #pragma unroll
           for (int i = 0; i < 64; ++i) o[i] = 0.f;
+#pragma unroll
           for (int j = 0; j < V; ++j) {
             const int rj = p0 + j;
             const float w = dots[j] * inv;
@@ -373,8 +386,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
             float t[32];
             tmem_ld_x32(tl + kT_ColR + 32 * cb, t);
             tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(b1 + 32 * cb);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = gelu_erf(t[i] + b1[32 * cb + i]);
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = b4[i];
+              t[4 * i] = gelu_erf(t[4 * i] + bb.x); t[4 * i + 1] = gelu_erf(t[4 * i + 1] + bb.y);
+              t[4 * i + 2] = gelu_erf(t[4 * i + 2] + bb.z); t[4 * i + 3] = gelu_erf(t[4 * i + 3] + bb.w);
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) store_a8(OA, 128, r, 32 * cb + 8 * u, pack8_bf16(t + 8 * u));
           }
@@ -433,6 +451,39 @@ struct MArgs {
   const int32_t* act_pid;   // already offset by `first`
   float* raw;               // (P, 4)
 };
+
+// Hidden-layer epilogue: 256 accumulator columns of this thread's row -> (+bias, ReLU) -> bf16 A
+// operand.  64 columns per TMEM round trip, biases as 128-bit broadcast loads, everything
+// compile-time so the inner loops are branch-free.  Returns sum_j act_j * w_alpha_j when kAlpha.
+template <bool kRelu, bool kAlpha>
+__device__ __forceinline__ float epi_hidden(uint32_t tl, const float* __restrict__ b,
+                                            const float* __restrict__ w_alpha, uint8_t* HA, int r) {
+  float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int cb = 0; cb < 4; ++cb) {
+    float t[64];
+    tmem_ld_x32(tl + 64 * cb, *reinterpret_cast<float(*)[32]>(&t[0]));
+    tmem_ld_x32(tl + 64 * cb + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
+    tmem_ld_wait();
+    const float4* b4 = reinterpret_cast<const float4*>(b + 64 * cb);
+    const float4* w4 = reinterpret_cast<const float4*>(w_alpha + 64 * cb);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 bb = b4[j];
+      float v0 = t[4 * j] + bb.x, v1 = t[4 * j + 1] + bb.y, v2 = t[4 * j + 2] + bb.z, v3 = t[4 * j + 3] + bb.w;
+      if (kRelu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+      if (kAlpha) {
+        const float4 ww = w4[j];
+        acc4[0] = fmaf(v0, ww.x, acc4[0]); acc4[1] = fmaf(v1, ww.y, acc4[1]);
+        acc4[2] = fmaf(v2, ww.z, acc4[2]); acc4[3] = fmaf(v3, ww.w, acc4[3]);
+      }
+      t[4 * j] = v0; t[4 * j + 1] = v1; t[4 * j + 2] = v2; t[4 * j + 3] = v3;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) store_a8(HA, 128, r, 64 * cb + 8 * u, pack8_bf16(t + 8 * u));
+  }
+  return (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -567,42 +618,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
 #pragma unroll
           for (int u = 0; u < 20; ++u) store_a8(XA, 128, r, 8 * u, valid ? __ldg(t1 + u) : make_uint4(0, 0, 0, 0));
         }
-        const float* b = (L < 8) ? bias + 256 * L : b_feat;
-#pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
-          float t[32];
-          tmem_ld_x32(tl + 32 * cb, t);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = t[j] + b[32 * cb + j];
-            if (L < 8) v = fmaxf(v, 0.f);
-            if (L == 7) alpha = fmaf(v, w_alpha[32 * cb + j], alpha);    // alpha_linear on the fp32 activations
-            t[j] = v;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) store_a8(HA, 128, r, 32 * cb + 8 * u, pack8_bf16(t + 8 * u));
-        }
+        // the layer kind is warp-uniform: pick a fully specialised epilogue (no per-element branches)
+        if (L == 7) alpha = epi_hidden<true, true>(tl, bias + 256 * 7, w_alpha, HA, r);   // + alpha_linear on fp32 acts
+        else if (L == 8) epi_hidden<false, false>(tl, b_feat, nullptr, HA, r);
+        else epi_hidden<true, false>(tl, bias + 256 * L, nullptr, HA, r);
         hand_over();
       }
       {
         // ---- views layer epilogue: relu -> rgb_linear on CUDA cores -> raw[pid] = (rgb, alpha)
         wait_d();
-        float rgb0 = b_tail[1], rgb1 = b_tail[2], rgb2 = b_tail[3];
+        float c0[2] = {0.f, 0.f}, c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          float t[32];
-          tmem_ld_x32(tl + 32 * cb, t);
+        for (int cb = 0; cb < 2; ++cb) {
+          float t[64];
+          tmem_ld_x32(tl + 64 * cb, *reinterpret_cast<float(*)[32]>(&t[0]));
+          tmem_ld_x32(tl + 64 * cb + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
           tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(b_views + 64 * cb);
+          const float4* r0 = reinterpret_cast<const float4*>(w_rgb + 64 * cb);
+          const float4* r1 = reinterpret_cast<const float4*>(w_rgb + 128 + 64 * cb);
+          const float4* r2 = reinterpret_cast<const float4*>(w_rgb + 256 + 64 * cb);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = fmaxf(t[j] + b_views[32 * cb + j], 0.f);
-            rgb0 = fmaf(v, w_rgb[32 * cb + j], rgb0);
-            rgb1 = fmaf(v, w_rgb[128 + 32 * cb + j], rgb1);
-            rgb2 = fmaf(v, w_rgb[256 + 32 * cb + j], rgb2);
+          for (int j = 0; j < 16; ++j) {
+            const float4 bb = b4[j], w0 = r0[j], w1 = r1[j], w2 = r2[j];
+            const float v0 = fmaxf(t[4 * j] + bb.x, 0.f), v1 = fmaxf(t[4 * j + 1] + bb.y, 0.f);
+            const float v2 = fmaxf(t[4 * j + 2] + bb.z, 0.f), v3 = fmaxf(t[4 * j + 3] + bb.w, 0.f);
+            c0[0] = fmaf(v0, w0.x, c0[0]); c0[1] = fmaf(v1, w0.y, c0[1]); c0[0] = fmaf(v2, w0.z, c0[0]); c0[1] = fmaf(v3, w0.w, c0[1]);
+            c1[0] = fmaf(v0, w1.x, c1[0]); c1[1] = fmaf(v1, w1.y, c1[1]); c1[0] = fmaf(v2, w1.z, c1[0]); c1[1] = fmaf(v3, w1.w, c1[1]);
+            c2[0] = fmaf(v0, w2.x, c2[0]); c2[1] = fmaf(v1, w2.y, c2[1]); c2[0] = fmaf(v2, w2.z, c2[0]); c2[1] = fmaf(v3, w2.w, c2[1]);
           }
         }
-        if (valid) reinterpret_cast<float4*>(a.raw)[a.act_pid[i]] = make_float4(rgb0, rgb1, rgb2, alpha + b_tail[0]);
+        if (valid)
+          reinterpret_cast<float4*>(a.raw)[a.act_pid[i]] =
+              make_float4(c0[0] + c0[1] + b_tail[1], c1[0] + c1[1] + b_tail[2], c2[0] + c2[1] + b_tail[3], alpha + b_tail[0]);
       }
     }
   }
@@ -700,7 +748,7 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
                                   const int32_t* act_pid, int64_t first, float* raw, void* workspace,
                                   void* stream) {
   using namespace mps;
-  MPS_REQUIRE(count >= 0 && n_views >= 2 && n_views <= MPSNERF_MAX_VIEWS);
+  MPS_REQUIRE(count >= 0 && n_views >= 2 && n_views <= 4);   // tensor-core path: 2..4 input views (fp32 path: up to 8)
   if (count == 0) return MPSNERF_OK;
   MPS_REQUIRE(tokens && xc && packed && act_pid && raw && workspace);
   MPS_REQUIRE(ld == MPSNERF_TOKEN_LD);
@@ -714,7 +762,9 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
 
   static bool attr_done = false;     // idempotent attribute set; benign if raced
   if (!attr_done) {
-    MPS_CUDA(cudaFuncSetAttribute(xformer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT_Smem));
+    MPS_CUDA(cudaFuncSetAttribute(xformer_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT_Smem));
+    MPS_CUDA(cudaFuncSetAttribute(xformer_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT_Smem));
+    MPS_CUDA(cudaFuncSetAttribute(xformer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT_Smem));
     MPS_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kM_Smem));
     attr_done = true;
   }
@@ -723,7 +773,9 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
     const int ppt = 128 / n_views;
     int64_t tiles = (count + ppt - 1) / ppt;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    xformer_tc_kernel<<<grid, kTcThreads, kT_Smem, st>>>(ta);
+    if (n_views == 2) xformer_tc_kernel<2><<<grid, kTcThreads, kT_Smem, st>>>(ta);
+    else if (n_views == 3) xformer_tc_kernel<3><<<grid, kTcThreads, kT_Smem, st>>>(ta);
+    else xformer_tc_kernel<4><<<grid, kTcThreads, kT_Smem, st>>>(ta);
     MPS_LAUNCH_CHECK();
   }
   {

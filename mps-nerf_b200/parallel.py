@@ -1,0 +1,49 @@
+"""Ray sharding across the GPUs of one node.
+
+Rays (and density-grid points) are independent given replicated read-only state, so the render
+path needs no exchange step: every rank renders a contiguous block of the ray set.  The only
+collectives are optional: assembling the frame on every rank (all_gather of 20 B/ray) and the
+max-over-ranks timing used by bench.py.  Works with any torch.distributed backend (NCCL on the
+B200 box, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def ray_block(n_rays, rank, world):
+    """[start, stop) of rank's contiguous block; blocks differ by at most one ray."""
+    base, rem = divmod(n_rays, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def render_sharded(render_fn, rays, near, far, **kw):
+    """Render this rank's block of ``rays (B,2,N,3)`` with ``render_fn`` (= run_nerf_batch.render).
+
+    Returns ([rgb, disp, acc, extras] of the block, (start, stop)).
+    """
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    s, e = ray_block(rays.shape[2], rank, world)
+    return render_fn(rays=rays[:, :, s:e], near=near[:, s:e], far=far[:, s:e], **kw), (s, e)
+
+
+def gather_frame(block, n_rays):
+    """all_gather per-ray outputs ``block (B, n_local, ...)`` into the full ``(B, n_rays, ...)`` frame."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return block
+    world = dist.get_world_size()
+    sizes = [ray_block(n_rays, r, world) for r in range(world)]
+    width = max(e - s for s, e in sizes)
+    pad = torch.zeros(block.shape[0], width, *block.shape[2:], dtype=block.dtype, device=block.device)
+    pad[:, :block.shape[1]] = block
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:, :e - s] for p, (s, e) in zip(parts, sizes)], dim=1)
+
+
+def max_over_ranks(value, device):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,64 @@
+"""World-size-2 gloo test of the ray-sharding host logic (no GPU needed: the render function is
+a stand-in, the product render has no CPU path)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_render(rays, near, far, **kw):
+    o, d = rays[:, 0], rays[:, 1]
+    rgb = o + d * near
+    acc = (d * far).sum(-1)
+    return [rgb, acc * 2, acc, {}]
+
+
+def _worker(rank, world, port, n_rays, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mpsnerf_b200 import parallel
+    g = torch.Generator().manual_seed(0)
+    rays = torch.randn(1, 2, n_rays, 3, generator=g)
+    near, far = torch.rand(1, n_rays, 1, generator=g), torch.rand(1, n_rays, 1, generator=g) + 1
+    (rgb, disp, acc, _), (s, e) = parallel.render_sharded(_fake_render, rays, near, far)
+    assert rgb.shape[1] == e - s
+    full_rgb = parallel.gather_frame(rgb, n_rays)
+    full_acc = parallel.gather_frame(acc, n_rays)
+    ref = _fake_render(rays, near, far)
+    assert torch.equal(full_rgb, ref[0]) and torch.equal(full_acc, ref[2])
+    assert parallel.max_over_ranks(rank + 1.5, "cpu") == world + 0.5
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put(rank)
+
+
+def test_ray_blocks_partition():
+    from mpsnerf_b200.parallel import ray_block
+    for n in (0, 1, 7, 262144, 1000001):
+        for w in (1, 2, 3, 8):
+            blocks = [ray_block(n, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_render_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1001, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(out.get(timeout=5) for _ in range(2)) == [0, 1]
