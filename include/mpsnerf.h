@@ -159,6 +159,15 @@ int mpsnerf_composite(const float* raw, const float* rays, int64_t n_rays, int32
 int mpsnerf_selftest_umma(const uint16_t* a, const uint8_t* b_packed, float* d, int N, int K,
                           void* stream);
 
+/* Same diagnostic with the A operand staged in tensor memory at column `acol` (tcgen05.st +
+ * TS-form MMA); acol >= N, acol % 8 == 0, acol + K/2 <= 512. */
+int mpsnerf_selftest_umma_ts(const uint16_t* a, const uint8_t* b_packed, float* d, int N, int K,
+                             int acol, void* stream);
+
+/* Debug: with MPSNERF_TC_PROF=1 the tensor-core kernels accumulate per-role cycle counters
+ * (see csrc/dense_tc.cu); this copies the 2 x 8 counters to the host and clears them. */
+int mpsnerf_debug_read_prof(unsigned long long* host_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,8 @@ SIGNATURES = {
     "mpsnerf_composite": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mpsnerf_selftest_umma_ts": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mpsnerf_debug_read_prof": (c_int, [c_void_p]),
 }
 
 _lib = None

@@ -2,24 +2,30 @@
 // and the canonical NeRF MLP ("M").  Restates lib/transformer.py:13-86 and
 // lib/skinnning_batch.py:438-473 with bf16 operands and fp32 accumulation.
 //
-// Common structure (one persistent CTA per SM, 192 threads):
-//   warps 0-3  epilogue: thread r owns TMEM lane r = row r of the 128-row tile.  They turn
+// Structure (one persistent CTA per SM, 320 threads):
+//   warps 0-7  epilogue, 256 threads: thread (r = tid & 127, half = tid >> 7) owns half of the
+//              columns of row r (TMEM lane r; warps w and w+4 share lane quarter w & 3).  They turn
 //              accumulators into the next A operand (bias / ReLU / GELU / LayerNorm / attention)
-//              written straight into the SWIZZLE_128B K-major smem layout the MMA reads;
-//   warp 4     weight producer: one thread streams the pre-swizzled weight chunks with bulk
-//              async copies (TMA engine) into an mbarrier ring, in consumption order;
-//   warp 5     MMA issuer: one thread issues tcgen05.mma (M = 128) and commits to mbarriers.
-// Activations never leave the SM between layers; per tile only the inputs are read and the
-// outputs written.  MMA <-> epilogue hand-over is a pair of mbarriers (a_bar: "A operand
-// ready", 128 arrivals; d_bar: "accumulator ready", tcgen05.commit).
+//              and store it, bf16-packed, back into TENSOR MEMORY (tcgen05.st);
+//   warp 8     weight producer: one thread streams the pre-swizzled weight chunks with bulk
+//              async copies (TMA engine) into an mbarrier ring, in consumption order
+//              (multicast across the kC CTAs of a cluster);
+//   warp 9     MMA issuer: one thread issues TS-form tcgen05.mma (A from TMEM, B from smem, M = 128).
+// Activations never leave the SM between layers and never touch shared memory: shared memory
+// holds only the weight ring (6-7 chunks in flight), which is what hides the L2 latency.
+// MMA <-> epilogue hand-over is a pair of mbarriers (a_bar: "A operand ready", 256 arrivals;
+// d_bar: "accumulator ready", tcgen05.commit).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace mps {
 using namespace umma;
 
-constexpr int kTcThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kTcThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kProdWarp = 8, kMmaWarp = 9;
 
 // ---- blob layout (must match mps-nerf_b200/pack.py)
 constexpr uint32_t kQkvChunk = 192 * 128, kWoChunk = 160 * 128, kW1Chunk = 128 * 128, kW2Chunk = 160 * 128;
@@ -33,9 +39,17 @@ static_assert(kTLayerBytes == 466944 && kMBytes == 1425408, "blob layout drifted
 
 constexpr int kTokLd = 160;   // bf16 row stride of tok0 / tok1 handed from T to M
 
-// ------------------------------------------------------------------------------------------
-// small shared pieces
-// ------------------------------------------------------------------------------------------
+// Optional in-kernel cycle accounting (MPSNERF_TC_PROF=1): per kernel 8 counters summed over CTAs:
+// 0 epilogue wait-for-MMA, 1 epilogue work, 2 tile load, 3 MMA wait-for-A, 4 MMA wait-for-weights,
+// 5 MMA thread total, 6 producer wait-for-free-slot, 7 tiles.  Read with mpsnerf_debug_read_prof().
+__device__ unsigned long long g_prof[2][8];
+struct Prof {
+  bool on;
+  long long t;
+  __device__ __forceinline__ void start() { if (on) t = clock64(); }
+  __device__ __forceinline__ void stop(long long& acc) { if (on) { const long long n = clock64(); acc += n - t; t = n; } }
+};
+
 struct Pipe {            // barriers of one CTA (in dynamic smem)
   uint64_t full[8];
   uint64_t empty[8];
@@ -57,31 +71,85 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
-__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
-  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// epilogue-side helpers shared by both kernels
+__device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpiThreads); }
+
+template <int kSlots, uint32_t kSlotBytes, int kC>
+struct Producer {            // used by the single producer thread
+  Pipe* pipe;
+  uint8_t* ring;
+  uint32_t crank;
+  uint32_t it = 0;
+  Prof pf;
+  long long acc_e = 0;
+  __device__ __forceinline__ void push(const uint8_t*& src, uint32_t bytes) {
+    const uint32_t slot = it % kSlots;
+    pf.start();
+    mbar_wait(&pipe->empty[slot], ((it / kSlots) & 1) ^ 1);
+    pf.stop(acc_e);
+    mbar_arrive_expect_tx(&pipe->full[slot], bytes);          // the whole chunk lands here (kC slices)
+    if (kC == 1) {
+      bulk_g2s(ring + slot * kSlotBytes, src, bytes, &pipe->full[slot]);
+    } else {
+      const uint32_t slice = bytes / kC;
+      bulk_g2s_mc(ring + slot * kSlotBytes + crank * slice, src + crank * slice, slice, &pipe->full[slot],
+                  (uint16_t)((1u << kC) - 1u));
+    }
+    src += bytes;
+    ++it;
+  }
+};
+
+template <int kSlots, uint32_t kSlotBytes, int kC>
+struct Consumer {            // used by the single MMA thread
+  Pipe* pipe;
+  uint32_t ring_addr;
+  uint32_t it = 0, g = 0;
+  Prof pf;
+  long long acc_a = 0, acc_w = 0;
+  __device__ __forceinline__ void wait_a() { pf.start(); mbar_wait(&pipe->a_bar, g & 1); pf.stop(acc_a); tc_fence_after(); }
+  __device__ __forceinline__ void done() { mma_commit(&pipe->d_bar); ++g; }
+  __device__ __forceinline__ uint32_t slot_wait() {
+    const uint32_t slot = it % kSlots;
+    pf.start();
+    mbar_wait(&pipe->full[slot], (it / kSlots) & 1);
+    pf.stop(acc_w);
+    tc_fence_after();
+    return ring_addr + slot * kSlotBytes;
+  }
+  __device__ __forceinline__ void slot_free() {
+    if (kC == 1) mma_commit(&pipe->empty[it % kSlots]);
+    else mma_commit_mc(&pipe->empty[it % kSlots], (uint16_t)((1u << kC) - 1u));
+    ++it;
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // T: cross-view transformer.  Tile = ppt = 128 / V points, row r = (point r / V, token r % V).
-// TMEM columns: X [0,160) fp32 residual stream (the out-proj and FF2 GEMMs accumulate into it,
-// which is the residual add; their biases are deferred, see pack.py), R [160,352) scratch
-// accumulator (q|k|v of one head, or the FF hidden layer).
+// TMEM columns:
+//   X  [0,160)    fp32 residual stream; the out-proj and FF2 GEMMs accumulate into it (that IS the
+//                 residual add; their biases are deferred, see pack.py)
+//   R  [160,352)  scratch accumulator: q|k|v of one head (192) or the FF hidden layer (128)
+//   YT [352,432)  LayerNorm output, bf16 x2 per column (K = 160)           -> A of qkv / FF1
+//   OT [432,496)  attention output of one head (K = 64, 32 cols) or GELU(FF hidden) (K = 128, 64 cols)
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kT_YA = 0;                       // LN output, A operand, 3 chunks
-constexpr uint32_t kT_OA = kT_YA + 3 * 16384;       // attention output (4 chunks = 4 heads); FF hidden aliases chunks 0-1
-constexpr uint32_t kT_KX = kT_OA + 4 * 16384;       // k of the current head, fp16 [128][64], unit-swizzled
+constexpr uint32_t kT_ColX = 0, kT_ColR = 160, kT_ColY = 352, kT_ColO = 432;
+constexpr uint32_t kT_KX = 0;                      // k of the current head, fp16 [128][64], unit-swizzled
 constexpr uint32_t kT_VX = kT_KX + 16384;
-constexpr uint32_t kT_RING = kT_VX + 16384;
-constexpr int kT_Slots = 3;
+constexpr uint32_t kT_PD = kT_VX + 16384;          // partial q.k dots  float[2][128][4]
+constexpr uint32_t kT_LS = kT_PD + 4096;           // LayerNorm partial sums float[2][2][128]
+constexpr uint32_t kT_RING = kT_LS + 2048;         // 1024-aligned: 16384*2 + 4096 + 2048 = 38912 = 38 * 1024
+constexpr int kT_Slots = 7;
 constexpr uint32_t kT_SlotBytes = kQkvChunk;
 constexpr uint32_t kT_FP = kT_RING + kT_Slots * kT_SlotBytes;
-constexpr uint32_t kT_PIPE = kT_FP + kTFloats * 4;
+constexpr uint32_t kT_PIPE = kT_FP + ((kTFloats * 4 + 15) / 16) * 16;
 constexpr uint32_t kT_Smem = kT_PIPE + sizeof(Pipe);
-constexpr uint32_t kT_ColX = 0, kT_ColR = 160;
+static_assert(kT_RING % 1024 == 0 && kT_SlotBytes % 1024 == 0, "ring slots must be 1024-byte aligned");
 static_assert(kT_Smem <= 232448 - 1024, "T kernel shared memory over budget");
 
 struct TArgs {
@@ -92,54 +160,64 @@ struct TArgs {
   const uint8_t* blob;
   __nv_bfloat16* tok0;   // (count, 160)
   __nv_bfloat16* tok1;
+  int prof;
 };
 
-// LayerNorm over the 155 real columns of x (+ optional pending bias), result -> bf16 A operand.
+// LayerNorm over the 155 real columns of a row whose 160 columns are split between two threads
+// (this thread: x[0..80) = columns 80*half ..; real columns: 80 or 75), result bf16-packed -> YT.
 // gamma/beta are zero in the 5 pad columns, so the pad of the operand is exactly zero.
-__device__ __forceinline__ void ln_to_operand(float (&x)[160], const float* __restrict__ pend,
-                                              const float* __restrict__ g, const float* __restrict__ b,
-                                              uint8_t* YA, int r) {
-  float s = 0.f;
+__device__ __forceinline__ void ln_to_tmem(float (&x)[80], const float* __restrict__ pend,
+                                           const float* __restrict__ g, const float* __restrict__ b, float* LS,
+                                           int r, int half, uint32_t tl) {
+  const int nreal = half ? 75 : 80;
   if (pend) {
-    const float4* p4 = reinterpret_cast<const float4*>(pend);
+    const float4* p4 = reinterpret_cast<const float4*>(pend + 80 * half);
 #pragma unroll
-    for (int c = 0; c < 40; ++c) {
+    for (int c = 0; c < 20; ++c) {
       const float4 t = p4[c];
       x[4 * c] += t.x; x[4 * c + 1] += t.y; x[4 * c + 2] += t.z; x[4 * c + 3] += t.w;
     }
   }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 155; ++c) s += x[c];
-  const float mean = s * (1.0f / 155.0f);
-  float v = 0.f;
+  for (int c = 0; c < 80; ++c) if (c < nreal) s[c & 3] += x[c];
+  LS[half * 128 + r] = (s[0] + s[1]) + (s[2] + s[3]);
+  epi_bar();
+  const float mean = (LS[r] + LS[128 + r]) * (1.0f / 155.0f);
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 155; ++c) { const float d = x[c] - mean; v = fmaf(d, d, v); }
-  const float rstd = rsqrtf(v * (1.0f / 155.0f) + 1e-5f);
+  for (int c = 0; c < 80; ++c) if (c < nreal) { const float d = x[c] - mean; v[c & 3] = fmaf(d, d, v[c & 3]); }
+  LS[256 + half * 128 + r] = (v[0] + v[1]) + (v[2] + v[3]);
+  epi_bar();
+  const float rstd = rsqrtf((LS[256 + r] + LS[384 + r]) * (1.0f / 155.0f) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g + 80 * half);
+  const float4* b4 = reinterpret_cast<const float4*>(b + 80 * half);
+  uint32_t pk[40];
 #pragma unroll
-  for (int c0 = 0; c0 < 160; c0 += 8) {
-    float y[8];
-    const float4 g0 = *reinterpret_cast<const float4*>(g + c0), g1 = *reinterpret_cast<const float4*>(g + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(b + c0), b1 = *reinterpret_cast<const float4*>(b + c0 + 4);
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = fmaf((x[c0 + i] - mean) * rstd, gg[i], bb[i]);
-    store_a8(YA, 128, r, c0, pack8_bf16(y));
+  for (int c = 0; c < 20; ++c) {
+    const float4 gg = g4[c], bb = b4[c];
+    const float y0 = fmaf((x[4 * c] - mean) * rstd, gg.x, bb.x), y1 = fmaf((x[4 * c + 1] - mean) * rstd, gg.y, bb.y);
+    const float y2 = fmaf((x[4 * c + 2] - mean) * rstd, gg.z, bb.z), y3 = fmaf((x[4 * c + 3] - mean) * rstd, gg.w, bb.w);
+    pk[2 * c] = pack_bf16x2(y0, y1);
+    pk[2 * c + 1] = pack_bf16x2(y2, y3);
   }
+#pragma unroll
+  for (int i = 0; i < 5; ++i)      // every TMEM access is aligned to its own width (here 8 columns)
+    tmem_st_x8(tl + kT_ColY + 40 * half + 8 * i, *reinterpret_cast<const uint32_t(*)[8]>(&pk[8 * i]));
+  tmem_st_wait();
 }
 
-__device__ __forceinline__ void load_x160(uint32_t taddr, float (&x)[160]) {
+__device__ __forceinline__ void load_x80(uint32_t taddr, float (&x)[80]) {
 #pragma unroll
-  for (int c = 0; c < 160; c += 32) {
-    float t[32];
-    tmem_ld_x32(taddr + c, t);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[c + i] = t[i];
-  }
+  for (int i = 0; i < 5; ++i) tmem_ld_x16(taddr + 16 * i, *reinterpret_cast<float(*)[16]>(&x[16 * i]));
+  tmem_ld_wait();
 }
 
-template <int kV>
+// kC = CTAs per cluster.  The kC CTAs of a cluster run the same program on neighbouring tiles and
+// share the weight stream: CTA j loads slice j of every chunk and multicasts it to all of them, so
+// each chunk crosses L2 -> SM once per cluster.  A ring slot is reused only after the MMA warps of
+// *all* kC CTAs have released it (empty barriers count kC arrivals, delivered by multicast commits).
+template <int kV, int kC>
 __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Pipe* pipe = reinterpret_cast<Pipe*>(smem + kT_PIPE);
@@ -148,297 +226,291 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
   constexpr int V = kV;
   constexpr int ppt = 128 / V;
   const int64_t ntiles = (a.count + ppt - 1) / ppt;
+  const uint32_t crank = (kC > 1) ? cluster_ctarank() : 0u;
+  const int64_t ncl = gridDim.x / kC, cid = blockIdx.x / kC;
 
   if (tid == 0) {
-    for (int i = 0; i < kT_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], 1); }
+    for (int i = 0; i < kT_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], kC); }
     mbar_init(&pipe->a_bar, kEpiThreads);
     mbar_init(&pipe->d_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 5) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
   {
     const float* src = reinterpret_cast<const float*>(a.blob + kFloatOff);
     for (int i = tid; i < kTFloats; i += kTcThreads) FP[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
+  if (kC > 1) cluster_sync_all();      // peers' barriers are initialised before any multicast touches them
   tc_fence_after();
   const uint32_t tm = pipe->tmem_base;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     // ================= weight producer =================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      Producer<kT_Slots, kT_SlotBytes, kC> P{pipe, smem + kT_RING, crank};
+      P.pf = Prof{a.prof != 0, 0};
+      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {   // cluster-uniform trip count
         for (int l = 0; l < 2; ++l) {
           const uint8_t* src = a.blob + (size_t)l * kTLayerBytes;
-          auto push = [&](uint32_t bytes) {
-            const uint32_t slot = it % kT_Slots;
-            mbar_wait(&pipe->empty[slot], ((it / kT_Slots) & 1) ^ 1);
-            mbar_arrive_expect_tx(&pipe->full[slot], bytes);
-            bulk_g2s(smem + kT_RING + slot * kT_SlotBytes, src, bytes, &pipe->full[slot]);
-            src += bytes;
-            ++it;
-          };
-          for (int c = 0; c < 3; ++c) push(kQkvChunk);
-          for (int h = 1; h < 4; ++h) { push(kWoChunk); for (int c = 0; c < 3; ++c) push(kQkvChunk); }
-          push(kWoChunk);
-          for (int c = 0; c < 3; ++c) push(kW1Chunk);
-          for (int c = 0; c < 2; ++c) push(kW2Chunk);
+          for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);
+          for (int h = 1; h < 4; ++h) { P.push(src, kWoChunk); for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk); }
+          P.push(src, kWoChunk);
+          for (int c = 0; c < 3; ++c) P.push(src, kW1Chunk);
+          for (int c = 0; c < 2; ++c) P.push(src, kW2Chunk);
         }
       }
+      if (a.prof) atomicAdd(&g_prof[0][6], (unsigned long long)P.acc_e);
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      uint32_t it = 0, g = 0;
-      const uint32_t sYA = smem_u32(smem + kT_YA), sOA = smem_u32(smem + kT_OA), sRing = smem_u32(smem + kT_RING);
-      auto wait_a = [&]() { mbar_wait(&pipe->a_bar, g & 1); tc_fence_after(); };
-      auto done = [&]() { mma_commit(&pipe->d_bar); ++g; };
-      auto slot_wait = [&]() -> uint32_t {
-        const uint32_t slot = it % kT_Slots;
-        mbar_wait(&pipe->full[slot], (it / kT_Slots) & 1);
-        tc_fence_after();
-        return sRing + slot * kT_SlotBytes;
-      };
-      auto slot_free = [&]() { mma_commit(&pipe->empty[it % kT_Slots]); ++it; };
-      // Y (K = 160: 10 k-steps over 3 chunks) x weight chunks with N rows -> D
-      auto gemm_y = [&](uint32_t dcol, int N, int nchunks) {
+      Consumer<kT_Slots, kT_SlotBytes, kC> Cn{pipe, smem_u32(smem + kT_RING)};
+      Cn.pf = Prof{a.prof != 0, 0};
+      const long long t_begin = clock64();
+      // A (TMEM, `ksteps` K=16 steps starting at column acol) x weight chunks with N rows -> D column dcol
+      auto gemm = [&](uint32_t dcol, uint32_t acol, int ksteps, int N, bool accumulate) {
         const uint32_t idesc = instr_desc_bf16(N);
-        for (int c = 0; c < nchunks; ++c) {
-          const uint32_t b0 = slot_wait();
+        for (int k0 = 0; k0 < ksteps; k0 += 4) {
+          const uint32_t b0 = Cn.slot_wait();
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            const int ks = c * 4 + k4;
-            if (ks < 10) mma_bf16_ss(tm + dcol, smem_desc_sw128(sYA + c * 16384 + k4 * 32), smem_desc_sw128(b0 + k4 * 32), idesc, ks > 0);
+            const int ks = k0 + k4;
+            if (ks < ksteps)
+              mma_bf16_ts(tm + dcol, tm + acol + ks * 8, smem_desc_sw128(b0 + k4 * 32), idesc, (accumulate || ks > 0) ? 1u : 0u);
           }
-          slot_free();
+          Cn.slot_free();
         }
       };
-      // A = chunk(s) of OA (64 K each) x weight chunk(s) with 160 rows, accumulated into X
-      auto gemm_into_x = [&](uint32_t a0, int nchunks) {
-        const uint32_t idesc = instr_desc_bf16(160);
-        for (int c = 0; c < nchunks; ++c) {
-          const uint32_t b0 = slot_wait();
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            mma_bf16_ss(tm + kT_ColX, smem_desc_sw128(a0 + c * 16384 + k4 * 32), smem_desc_sw128(b0 + k4 * 32), idesc, 1u);
-          slot_free();
-        }
-      };
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
         for (int l = 0; l < 2; ++l) {
-          wait_a(); gemm_y(kT_ColR, 192, 3); done();                        // q|k|v of head 0
+          Cn.wait_a(); gemm(kT_ColR, kT_ColY, 10, 192, false); Cn.done();           // q|k|v of head 0
           for (int h = 1; h < 4; ++h) {
-            wait_a();
-            gemm_into_x(sOA + (h - 1) * 16384, 1);                          // x += o_{h-1} Wo_{h-1}^T
-            gemm_y(kT_ColR, 192, 3);                                        // q|k|v of head h
-            done();
+            Cn.wait_a();
+            gemm(kT_ColX, kT_ColO, 4, 160, true);                                    // x += o_{h-1} Wo_{h-1}^T
+            gemm(kT_ColR, kT_ColY, 10, 192, false);                                  // q|k|v of head h
+            Cn.done();
           }
-          wait_a(); gemm_into_x(sOA + 3 * 16384, 1); done();
-          wait_a(); gemm_y(kT_ColR, 128, 3); done();                        // FF hidden
-          wait_a(); gemm_into_x(sOA, 2); done();                            // x += gelu(.) W2^T
+          Cn.wait_a(); gemm(kT_ColX, kT_ColO, 4, 160, true); Cn.done();
+          Cn.wait_a(); gemm(kT_ColR, kT_ColY, 10, 128, false); Cn.done();            // FF hidden
+          Cn.wait_a(); gemm(kT_ColX, kT_ColO, 8, 160, true); Cn.done();              // x += gelu(.) W2^T
         }
+      }
+      if (a.prof) {
+        atomicAdd(&g_prof[0][3], (unsigned long long)Cn.acc_a);
+        atomicAdd(&g_prof[0][4], (unsigned long long)Cn.acc_w);
+        atomicAdd(&g_prof[0][5], (unsigned long long)(clock64() - t_begin));
       }
     }
   } else {
     // ================= epilogue warps =================
-    const int r = tid;
-    uint8_t* YA = smem + kT_YA;
-    uint8_t* OA = smem + kT_OA;
+    const int r = tid & 127, half = tid >> 7;
     uint8_t* KX = smem + kT_KX;
     uint8_t* VX = smem + kT_VX;
-    const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
+    float* PD = reinterpret_cast<float*>(smem + kT_PD);
+    float* LS = reinterpret_cast<float*>(smem + kT_LS);
+    const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t g = 0;
-    auto hand_over = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(&pipe->a_bar); };
-    auto wait_d = [&]() { mbar_wait(&pipe->d_bar, g & 1); ++g; tc_fence_after(); };
+    Prof pf{a.prof != 0 && tid == 0, 0};
+    long long acc_d = 0, acc_tl = 0, n_tiles = 0;
+    const long long t_begin = clock64();
+    auto hand_over = [&]() { tc_fence_before(); mbar_arrive(&pipe->a_bar); };
+    auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar, g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
     constexpr int rows = ppt * V;
     const int p0 = (r < rows) ? (r / V) * V : 0;      // first row of this row's point (attention partners)
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
+      const int64_t tile = tbase + crank;              // tile >= ntiles: all rows invalid
       const int64_t pnt = tile * ppt + r / V;
       const int tok = r % V;
       const bool valid = (r < rows) && (pnt < a.count);
       {
-        // ---- tile load: tokens -> X (TMEM), LN1 of layer 0 -> YA
-        float x[160];
+        // ---- tile load: tokens -> X (TMEM), LN1 of layer 0 -> YT
+        pf.start();
+        float x[80];
         if (valid) {
-          const float4* src = reinterpret_cast<const float4*>(a.tokens + (pnt * V + tok) * (int64_t)a.ld);
+          const float4* src = reinterpret_cast<const float4*>(a.tokens + (pnt * V + tok) * (int64_t)a.ld + 80 * half);
 #pragma unroll
-          for (int c = 0; c < 40; ++c) {
+          for (int c = 0; c < 20; ++c) {
             const float4 t = __ldg(src + c);
             x[4 * c] = t.x; x[4 * c + 1] = t.y; x[4 * c + 2] = t.z; x[4 * c + 3] = t.w;
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 160; ++c) x[c] = 0.f;
+          for (int c = 0; c < 80; ++c) x[c] = 0.f;
         }
+        {
+          uint32_t xb[80];
 #pragma unroll
-        for (int c = 0; c < 160; c += 16) {
-          float t[16];
+          for (int c = 0; c < 80; ++c) xb[c] = __float_as_uint(x[c]);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) t[i] = x[c + i];
-          tmem_st_x16(tl + kT_ColX + c, t);
+          for (int i = 0; i < 5; ++i) tmem_st_u16(tl + kT_ColX + 80 * half + 16 * i, xb + 16 * i);   // 16-aligned
         }
-        tmem_st_wait();
-        ln_to_operand(x, nullptr, FP, FP + 160, YA, r);
+        ln_to_tmem(x, nullptr, FP, FP + 160, LS, r, half, tl);
+        pf.stop(acc_tl);
         hand_over();
       }
       for (int l = 0; l < 2; ++l) {
         const float* fp = FP + l * kTLayerFloats;   // ln1_g ln1_b pend_in ln2_g ln2_b pend_mid b1
         for (int h = 0; h < 4; ++h) {
           wait_d();
-          // ---- attention of head h (lib/transformer.py:59-71): R = [q | k | v], 64 columns each
+          // ---- attention of head h (lib/transformer.py:59-71): R = [q | k | v], 64 columns each.
+          // half 0 publishes k, half 1 publishes v (fp16, unit-swizzled rows of 128 B)
           {
-            float t[32];
+            float t[64];
+            tmem_ld_x32(tl + kT_ColR + 64 + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
+            tmem_ld_x32(tl + kT_ColR + 64 + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
+            tmem_ld_wait();
+            uint8_t* dst = (half == 0 ? KX : VX) + r * 128;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {      // k -> KX, v -> VX as fp16
-#pragma unroll
-              for (int part = 0; part < 2; ++part) {
-                tmem_ld_x32(tl + kT_ColR + 64 + 64 * part + 32 * half, t);
-                tmem_ld_wait();
-                uint8_t* dst = (part == 0 ? KX : VX) + r * 128;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const uint4 pk = make_uint4(pack_h2(t[8 * u], t[8 * u + 1]), pack_h2(t[8 * u + 2], t[8 * u + 3]),
-                                              pack_h2(t[8 * u + 4], t[8 * u + 5]), pack_h2(t[8 * u + 6], t[8 * u + 7]));
-                  *reinterpret_cast<uint4*>(dst + (((half * 4 + u) ^ (r & 7)) << 4)) = pk;
-                }
-              }
+            for (int u = 0; u < 8; ++u) {
+              const uint4 pk = make_uint4(pack_h2(t[8 * u], t[8 * u + 1]), pack_h2(t[8 * u + 2], t[8 * u + 3]),
+                                          pack_h2(t[8 * u + 4], t[8 * u + 5]), pack_h2(t[8 * u + 6], t[8 * u + 7]));
+              *reinterpret_cast<uint4*>(dst + ((u ^ (r & 7)) << 4)) = pk;
             }
           }
-          named_bar_sync(1, kEpiThreads);
-          float q[64];
-          {
-            float t[32];
-            tmem_ld_x32(tl + kT_ColR, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) q[i] = t[i];
-            tmem_ld_x32(tl + kT_ColR + 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) q[32 + i] = t[i];
-          }
-          float dots[V];
-          float mx = -1e30f;
+          float q[32];
+          tmem_ld_x32(tl + kT_ColR + 32 * half, q);
+          tmem_ld_wait();
+          epi_bar();
+          // partial dots over this thread's 32 of the 64 head dims
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const int rj = p0 + j;
             const uint8_t* src = KX + rj * 128;
-            float d = 0.f;
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(src + ((u ^ (rj & 7)) << 4));
+            for (int u = 0; u < 4; ++u) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(src + (((4 * half + u) ^ (rj & 7)) << 4));
               const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 f = __half22float2(h2[i]);
-                d = fmaf(q[8 * u + 2 * i], f.x, d);
-                d = fmaf(q[8 * u + 2 * i + 1], f.y, d);
+                d[i] = fmaf(q[8 * u + 2 * i], f.x, d[i]);
+                d[i] = fmaf(q[8 * u + 2 * i + 1], f.y, d[i]);
               }
             }
-            dots[j] = d * 0.125f;
-            mx = fmaxf(mx, dots[j]);
+            PD[(half * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
+          }
+          epi_bar();
+          float w[V];
+          float mx = -1e30f;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            w[j] = (PD[r * 4 + j] + PD[(128 + r) * 4 + j]) * 0.125f;      // dim_head ** -0.5
+            mx = fmaxf(mx, w[j]);
           }
           float den = 0.f;
 #pragma unroll
-          for (int j = 0; j < V; ++j) { dots[j] = __expf(dots[j] - mx); den += dots[j]; }
+          for (int j = 0; j < V; ++j) { w[j] = __expf(w[j] - mx); den += w[j]; }
           const float inv = 1.0f / den;
-          float o[64];
+          float o[32];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) o[i] = 0.f;
+          for (int i = 0; i < 32; ++i) o[i] = 0.f;
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const int rj = p0 + j;
-            const float w = dots[j] * inv;
+            const float wj = w[j] * inv;
             const uint8_t* src = VX + rj * 128;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(src + ((u ^ (rj & 7)) << 4));
+            for (int u = 0; u < 4; ++u) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(src + (((4 * half + u) ^ (rj & 7)) << 4));
               const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 f = __half22float2(h2[i]);
-                o[8 * u + 2 * i] = fmaf(w, f.x, o[8 * u + 2 * i]);
-                o[8 * u + 2 * i + 1] = fmaf(w, f.y, o[8 * u + 2 * i + 1]);
+                o[8 * u + 2 * i] = fmaf(wj, f.x, o[8 * u + 2 * i]);
+                o[8 * u + 2 * i + 1] = fmaf(wj, f.y, o[8 * u + 2 * i + 1]);
               }
             }
           }
+          uint32_t pk[16];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) store_a8(OA + h * 16384, 128, r, 8 * u, pack8_bf16(o + 8 * u));
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+          tmem_st_u16(tl + kT_ColO + 16 * half, pk);
+          tmem_st_wait();
           hand_over();
         }
         {
-          // ---- x (+ deferred biases) -> LN2 -> YA
+          // ---- x (+ deferred biases) -> LN2 -> YT
           wait_d();
-          float x[160];
-          load_x160(tl + kT_ColX, x);
-          ln_to_operand(x, fp + 800, fp + 480, fp + 640, YA, r);
+          float x[80];
+          load_x80(tl + kT_ColX + 80 * half, x);
+          ln_to_tmem(x, fp + 800, fp + 480, fp + 640, LS, r, half, tl);
           hand_over();
         }
         {
-          // ---- FF hidden: GELU(acc + b1) -> bf16 operand (K = 128, aliases OA chunks 0-1)
+          // ---- FF hidden: GELU(acc + b1) -> bf16 operand (K = 128 -> 64 packed columns)
           wait_d();
-          const float* b1 = fp + 960;
+          float t[64];
+          tmem_ld_x32(tl + kT_ColR + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
+          tmem_ld_x32(tl + kT_ColR + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(fp + 960 + 64 * half);
+          uint32_t pk[32];
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
-            float t[32];
-            tmem_ld_x32(tl + kT_ColR + 32 * cb, t);
-            tmem_ld_wait();
-            const float4* b4 = reinterpret_cast<const float4*>(b1 + 32 * cb);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 bb = b4[i];
-              t[4 * i] = gelu_erf(t[4 * i] + bb.x); t[4 * i + 1] = gelu_erf(t[4 * i + 1] + bb.y);
-              t[4 * i + 2] = gelu_erf(t[4 * i + 2] + bb.z); t[4 * i + 3] = gelu_erf(t[4 * i + 3] + bb.w);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) store_a8(OA, 128, r, 32 * cb + 8 * u, pack8_bf16(t + 8 * u));
+          for (int i = 0; i < 16; ++i) {
+            const float4 bb = b4[i];
+            pk[2 * i] = pack_bf16x2(gelu_erf(t[4 * i] + bb.x), gelu_erf(t[4 * i + 1] + bb.y));
+            pk[2 * i + 1] = pack_bf16x2(gelu_erf(t[4 * i + 2] + bb.z), gelu_erf(t[4 * i + 3] + bb.w));
           }
+          tmem_st_u16(tl + kT_ColO + 32 * half, pk);
+          tmem_st_u16(tl + kT_ColO + 32 * half + 16, pk + 16);
+          tmem_st_wait();
           hand_over();
         }
         {
           wait_d();
-          float x[160];
-          load_x160(tl + kT_ColX, x);
+          float x[80];
+          load_x80(tl + kT_ColX + 80 * half, x);
           if (l == 0) {
             const float* f1 = FP + kTLayerFloats;        // layer 1: LN1 on x + pend_in
-            ln_to_operand(x, f1 + 320, f1, f1 + 160, YA, r);
+            ln_to_tmem(x, f1 + 320, f1, f1 + 160, LS, r, half, tl);
             hand_over();
           } else if (valid && tok < 2) {
             // ---- output tokens 0 (density branch) and 1 (colour branch), lib/skinnning_batch.py:441-442
-            const float* pend = FP + 2 * kTLayerFloats;
-            __nv_bfloat16* dst = (tok == 0 ? a.tok0 : a.tok1) + pnt * kTokLd;
+            const float4* p4 = reinterpret_cast<const float4*>(FP + 2 * kTLayerFloats + 80 * half);
+            uint4* dst = reinterpret_cast<uint4*>((tok == 0 ? a.tok0 : a.tok1) + pnt * kTokLd + 80 * half);
 #pragma unroll
-            for (int c0 = 0; c0 < 160; c0 += 8) {
-              float y[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = x[c0 + i] + pend[c0 + i];
-              *reinterpret_cast<uint4*>(dst + c0) = pack8_bf16(y);
+            for (int c = 0; c < 10; ++c) {
+              const float4 pa = p4[2 * c], pb = p4[2 * c + 1];
+              dst[c] = make_uint4(pack_bf16x2(x[8 * c] + pa.x, x[8 * c + 1] + pa.y), pack_bf16x2(x[8 * c + 2] + pa.z, x[8 * c + 3] + pa.w),
+                                  pack_bf16x2(x[8 * c + 4] + pb.x, x[8 * c + 5] + pb.y), pack_bf16x2(x[8 * c + 6] + pb.z, x[8 * c + 7] + pb.w));
             }
           }
         }
       }
+      ++n_tiles;
+    }
+    if (pf.on) {
+      atomicAdd(&g_prof[0][0], (unsigned long long)acc_d);
+      atomicAdd(&g_prof[0][1], (unsigned long long)(clock64() - t_begin - acc_d - acc_tl));
+      atomicAdd(&g_prof[0][2], (unsigned long long)acc_tl);
+      atomicAdd(&g_prof[0][7], (unsigned long long)n_tiles);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tm, 512);
+  if (kC > 1) cluster_sync_all();      // no CTA may exit while a peer can still multicast into it
+  if (warp == kMmaWarp) tmem_dealloc(tm, 512);
 }
 
 // ------------------------------------------------------------------------------------------
-// M: canonical NeRF MLP.  Tile = 128 points.  TMEM: one 256-column accumulator.
-// A operands: XA = [tok0 155 | 0 x5 | PE6(xc) 39 | 0] (K = 208, reused for tok1 after layer 5),
-// HA = hidden activations (K = 256).  Weight ring slots are half chunks (128 rows x 128 B).
+// M: canonical NeRF MLP.  Tile = 128 points.  TMEM columns:
+//   ACC [0,256)    accumulator
+//   HT  [256,384)  hidden activations, bf16 x2 per column (K = 256)
+//   XT  [384,496)  x = [tok0 155 | 0 x5 | PE6(xc) 39 | 0 x25] (K = 224, 14 K-steps);
+//                  reused for tok1 (K = 160) after layer 5
+// Shared memory holds only the weight ring (6 x 32 KB) and the fp32 parameter vectors.
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kM_XA = 0;
-constexpr uint32_t kM_HA = kM_XA + 4 * 16384;
-constexpr uint32_t kM_RING = kM_HA + 4 * 16384;
-constexpr int kM_Slots = 5;
-constexpr uint32_t kM_SlotBytes = 16384;
+constexpr uint32_t kM_ColAcc = 0, kM_ColH = 256, kM_ColX = 384;
+constexpr uint32_t kM_RING = 0;
+constexpr int kM_Slots = 6;
+constexpr uint32_t kM_SlotBytes = 32768;
 constexpr uint32_t kM_FP = kM_RING + kM_Slots * kM_SlotBytes;
-constexpr uint32_t kM_PIPE = kM_FP + kMFloats * 4;
+constexpr uint32_t kM_PART = kM_FP + ((kMFloats * 4 + 15) / 16) * 16;   // float[128][4]: alpha / rgb partials of half 1
+constexpr uint32_t kM_PIPE = kM_PART + 128 * 16;
 constexpr uint32_t kM_Smem = kM_PIPE + sizeof(Pipe);
 static_assert(kM_Smem <= 232448 - 1024, "M kernel shared memory over budget");
 
@@ -450,23 +522,26 @@ struct MArgs {
   const uint8_t* blob;
   const int32_t* act_pid;   // already offset by `first`
   float* raw;               // (P, 4)
+  int prof;
 };
 
-// Hidden-layer epilogue: 256 accumulator columns of this thread's row -> (+bias, ReLU) -> bf16 A
-// operand.  64 columns per TMEM round trip, biases as 128-bit broadcast loads, everything
-// compile-time so the inner loops are branch-free.  Returns sum_j act_j * w_alpha_j when kAlpha.
+// Hidden-layer epilogue of one thread: 128 accumulator columns (its half of the row) ->
+// (+bias, ReLU) -> bf16 x2 -> HT.  Everything compile-time so the inner loops are branch-free.
+// Returns this half's sum_j act_j * w_alpha_j when kAlpha.
 template <bool kRelu, bool kAlpha>
-__device__ __forceinline__ float epi_hidden(uint32_t tl, const float* __restrict__ b,
-                                            const float* __restrict__ w_alpha, uint8_t* HA, int r) {
+__device__ __forceinline__ float epi_hidden(uint32_t tl, int half, const float* __restrict__ b,
+                                            const float* __restrict__ w_alpha) {
   float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-  for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+  for (int cb = 0; cb < 2; ++cb) {
+    const int c0 = 128 * half + 64 * cb;
     float t[64];
-    tmem_ld_x32(tl + 64 * cb, *reinterpret_cast<float(*)[32]>(&t[0]));
-    tmem_ld_x32(tl + 64 * cb + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
+    tmem_ld_x32(tl + kM_ColAcc + c0, *reinterpret_cast<float(*)[32]>(&t[0]));
+    tmem_ld_x32(tl + kM_ColAcc + c0 + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
     tmem_ld_wait();
-    const float4* b4 = reinterpret_cast<const float4*>(b + 64 * cb);
-    const float4* w4 = reinterpret_cast<const float4*>(w_alpha + 64 * cb);
+    const float4* b4 = reinterpret_cast<const float4*>(b + c0);
+    const float4* w4 = reinterpret_cast<const float4*>(w_alpha + c0);
+    uint32_t pk[32];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float4 bb = b4[j];
@@ -477,106 +552,133 @@ __device__ __forceinline__ float epi_hidden(uint32_t tl, const float* __restrict
         acc4[0] = fmaf(v0, ww.x, acc4[0]); acc4[1] = fmaf(v1, ww.y, acc4[1]);
         acc4[2] = fmaf(v2, ww.z, acc4[2]); acc4[3] = fmaf(v3, ww.w, acc4[3]);
       }
-      t[4 * j] = v0; t[4 * j + 1] = v1; t[4 * j + 2] = v2; t[4 * j + 3] = v3;
+      pk[2 * j] = pack_bf16x2(v0, v1);
+      pk[2 * j + 1] = pack_bf16x2(v2, v3);
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) store_a8(HA, 128, r, 64 * cb + 8 * u, pack8_bf16(t + 8 * u));
+    tmem_st_u32(tl + kM_ColH + c0 / 2, pk);
   }
+  tmem_st_wait();
   return (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
 }
 
+// 80 packed columns of a bf16 token row (160 values), split between the two halves of the row
+__device__ __forceinline__ void token_to_tmem(const __nv_bfloat16* row, bool valid, int half, uint32_t taddr) {
+  uint32_t w[40];
+  const uint4* src = reinterpret_cast<const uint4*>(row) + 10 * half;     // 80 bf16 = 10 x 16 bytes per half
+#pragma unroll
+  for (int u = 0; u < 10; ++u) {
+    const uint4 t = valid ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+    w[4 * u] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) tmem_st_x8(taddr + 40 * half + 8 * i, *reinterpret_cast<const uint32_t(*)[8]>(&w[8 * i]));
+}
+
+// 32 elements (16 packed words) of the 39-wide positional code [x, sin(f0 x), cos(f0 x), ...]
+// (run_nerf_helpers.py:337-353; cos as sin(. + fl(pi/2))); elements >= 39 are zero padding.
+template <int kHalf>
+__device__ __forceinline__ void pe_words(const float (&xc)[3], uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int w2 = 0; w2 < 16; ++w2) {
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      constexpr int kBase = 32 * kHalf;
+      const int e = kBase + 2 * w2 + q;            // compile-time after unrolling
+      float val = 0.f;
+      if (e < 3) val = xc[e];
+      else if (e < 39) {
+        const int k = (e - 3) / 6, ch = (e - 3) % 3;
+        const bool is_cos = ((e - 3) % 6) >= 3;
+        val = sinf(fmaf(xc[ch], 3.14159265358979323846f * (float)(1 << k), is_cos ? 1.57079632679489661923f : 0.0f));
+      }
+      v[q] = val;
+    }
+    pk[w2] = pack_bf16x2(v[0], v[1]);
+  }
+}
+
+template <int kC>
 __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Pipe* pipe = reinterpret_cast<Pipe*>(smem + kM_PIPE);
   float* FP = reinterpret_cast<float*>(smem + kM_FP);
+  float* PART = reinterpret_cast<float*>(smem + kM_PART);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (a.count + 127) / 128;
+  const uint32_t crank = (kC > 1) ? cluster_ctarank() : 0u;
+  const int64_t ncl = gridDim.x / kC, cid = blockIdx.x / kC;
 
   if (tid == 0) {
-    for (int i = 0; i < kM_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], 1); }
+    for (int i = 0; i < kM_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], kC); }
     mbar_init(&pipe->a_bar, kEpiThreads);
     mbar_init(&pipe->d_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 5) { tmem_alloc(&pipe->tmem_base, 256); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
   {
     const float* src = reinterpret_cast<const float*>(a.blob + kFloatOff) + kTFloats;
     for (int i = tid; i < kMFloats; i += kTcThreads) FP[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
+  if (kC > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tm = pipe->tmem_base;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      Producer<kM_Slots, kM_SlotBytes, kC> P{pipe, smem + kM_RING, crank};
+      P.pf = Prof{a.prof != 0, 0};
+      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
         const uint8_t* src = a.blob + kTBytes;
-        constexpr int kItems = (kMBytes / kM_SlotBytes);      // the whole MLP section, in order
-        for (int i = 0; i < kItems; ++i) {
-          const uint32_t slot = it % kM_Slots;
-          mbar_wait(&pipe->empty[slot], ((it / kM_Slots) & 1) ^ 1);
-          mbar_arrive_expect_tx(&pipe->full[slot], kM_SlotBytes);
-          bulk_g2s(smem + kM_RING + slot * kM_SlotBytes, src, kM_SlotBytes, &pipe->full[slot]);
-          src += kM_SlotBytes;
-          ++it;
-        }
+        for (int i = 0; i < 40; ++i) P.push(src, 32768);      // L0..L7, feature: 256-row chunks
+        for (int i = 0; i < 7; ++i) P.push(src, 16384);       // views: 128-row chunks
       }
+      if (a.prof) atomicAdd(&g_prof[1][6], (unsigned long long)P.acc_e);
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
-      uint32_t it = 0, g = 0;
-      const uint32_t sXA = smem_u32(smem + kM_XA), sHA = smem_u32(smem + kM_HA), sRing = smem_u32(smem + kM_RING);
-      const uint32_t idesc = instr_desc_bf16(128);
-      auto wait_a = [&]() { mbar_wait(&pipe->a_bar, g & 1); tc_fence_after(); };
-      auto done = [&]() { mma_commit(&pipe->d_bar); ++g; };
-      // one K-chunk of A (at a0, `ksteps` valid K=16 steps) against `nhalves` 128-row weight halves
-      auto chunk = [&](uint32_t a0, int ksteps, int nhalves, bool first) {
-        for (int n = 0; n < nhalves; ++n) {
-          const uint32_t slot = it % kM_Slots;
-          mbar_wait(&pipe->full[slot], (it / kM_Slots) & 1);
-          tc_fence_after();
-          const uint32_t b0 = sRing + slot * kM_SlotBytes;
+      Consumer<kM_Slots, kM_SlotBytes, kC> Cn{pipe, smem_u32(smem + kM_RING)};
+      Cn.pf = Prof{a.prof != 0, 0};
+      const long long t_begin = clock64();
+      // A (TMEM at column acol, `ksteps` valid K=16 steps out of `chunks` weight chunks) -> ACC
+      auto gemm = [&](uint32_t acol, int ksteps, int chunks, int N, bool accumulate) {
+        const uint32_t idesc = instr_desc_bf16(N);
+        for (int c = 0; c < chunks; ++c) {
+          const uint32_t b0 = Cn.slot_wait();
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            if (k4 < ksteps)
-              mma_bf16_ss(tm + n * 128, smem_desc_sw128(a0 + k4 * 32), smem_desc_sw128(b0 + k4 * 32), idesc, (!first || k4 > 0) ? 1u : 0u);
-          mma_commit(&pipe->empty[slot]);
-          ++it;
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = 4 * c + k4;
+            if (ks < ksteps)
+              mma_bf16_ts(tm + kM_ColAcc, tm + acol + ks * 8, smem_desc_sw128(b0 + k4 * 32), idesc, (accumulate || ks > 0) ? 1u : 0u);
+          }
+          Cn.slot_free();
         }
       };
-      auto x_part = [&](int nhalves, int ksteps_total, bool first) {       // XA: 13 steps (x) or 10 (tok1)
-        const int nch = (ksteps_total + 3) / 4;
-        for (int c = 0; c < 4; ++c) {
-          const int ks = min(4, ksteps_total - 4 * c);
-          if (c < nch) chunk(sXA + c * 16384, ks, nhalves, first && c == 0);
-          else if (nhalves == 2) chunk(sXA + c * 16384, 0, nhalves, false);   // keep the weight stream in step
-        }
-      };
-      auto h_part = [&](int nhalves, bool first) {
-        for (int c = 0; c < 4; ++c) chunk(sHA + c * 16384, 4, nhalves, first && c == 0);
-      };
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        wait_a(); x_part(2, 13, true); done();                              // L0
-        for (int L = 1; L < 5; ++L) { wait_a(); h_part(2, true); done(); }  // L1..L4
-        wait_a(); x_part(2, 13, true); h_part(2, false); done();            // L5: [x | h]
-        for (int L = 6; L < 8; ++L) { wait_a(); h_part(2, true); done(); }  // L6, L7
-        wait_a(); h_part(2, true); done();                                  // feature
-        wait_a();                                                           // views: [tok1 | feature], N = 128
-        for (int c = 0; c < 3; ++c) chunk(sXA + c * 16384, c < 2 ? 4 : 2, 1, c == 0);
-        for (int c = 0; c < 4; ++c) chunk(sHA + c * 16384, 4, 1, false);
-        done();
+      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
+        Cn.wait_a(); gemm(kM_ColX, 14, 4, 256, false); Cn.done();                                   // L0
+        for (int L = 1; L < 5; ++L) { Cn.wait_a(); gemm(kM_ColH, 16, 4, 256, false); Cn.done(); }   // L1..L4
+        Cn.wait_a(); gemm(kM_ColX, 14, 4, 256, false); gemm(kM_ColH, 16, 4, 256, true); Cn.done();  // L5: [x | h]
+        for (int L = 6; L < 8; ++L) { Cn.wait_a(); gemm(kM_ColH, 16, 4, 256, false); Cn.done(); }   // L6, L7
+        Cn.wait_a(); gemm(kM_ColH, 16, 4, 256, false); Cn.done();                                   // feature
+        Cn.wait_a(); gemm(kM_ColX, 10, 3, 128, false); gemm(kM_ColH, 16, 4, 128, true); Cn.done();  // views: [tok1 | feature]
+      }
+      if (a.prof) {
+        atomicAdd(&g_prof[1][3], (unsigned long long)Cn.acc_a);
+        atomicAdd(&g_prof[1][4], (unsigned long long)Cn.acc_w);
+        atomicAdd(&g_prof[1][5], (unsigned long long)(clock64() - t_begin));
       }
     }
   } else {
-    const int r = tid;
-    uint8_t* XA = smem + kM_XA;
-    uint8_t* HA = smem + kM_HA;
-    const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
+    const int r = tid & 127, half = tid >> 7;
+    const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t g = 0;
-    auto hand_over = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(&pipe->a_bar); };
-    auto wait_d = [&]() { mbar_wait(&pipe->d_bar, g & 1); ++g; tc_fence_after(); };
+    Prof pf{a.prof != 0 && tid == 0, 0};
+    long long acc_d = 0, acc_tl = 0, n_tiles = 0;
+    const long long t_begin = clock64();
+    auto hand_over = [&]() { tc_fence_before(); mbar_arrive(&pipe->a_bar); };
+    auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar, g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
     const float* bias = FP;                       // 8 x 256
     const float* w_alpha = FP + 2048;
     const float* b_feat = FP + 2304;
@@ -584,79 +686,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
     const float* w_rgb = FP + 2688;               // 3 x 128
     const float* b_tail = FP + 3072;              // b_alpha, b_rgb[3]
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
+      const int64_t tile = tbase + crank;
       const int64_t i = tile * 128 + r;
       const bool valid = i < a.count;
       {
-        // ---- tile load: XA = [tok0 | 0 | PE6(xc) | 0]
-        const uint4* t0 = reinterpret_cast<const uint4*>(a.tok0 + (valid ? i : 0) * kTokLd);
-#pragma unroll
-        for (int u = 0; u < 20; ++u) store_a8(XA, 128, r, 8 * u, valid ? __ldg(t0 + u) : make_uint4(0, 0, 0, 0));
-        float pe[48];
+        // ---- tile load: XT = [tok0 | 0 | PE6(xc) | 0]; this thread: 40 token columns + 16 PE columns
+        pf.start();
+        token_to_tmem(a.tok0 + (valid ? i : 0) * kTokLd, valid, half, tl + kM_ColX);
         float xc[3] = {0.f, 0.f, 0.f};
         if (valid) { xc[0] = a.xc[3 * i]; xc[1] = a.xc[3 * i + 1]; xc[2] = a.xc[3 * i + 2]; }
-#pragma unroll
-        for (int e = 0; e < 48; ++e) {
-          float v = 0.f;
-          if (e < 3) v = xc[e];
-          else if (e < 39) {
-            const int k = (e - 3) / 6, ch = (e - 3) % 3;
-            const bool is_cos = ((e - 3) % 6) >= 3;
-            v = sinf(fmaf(xc[ch], 3.14159265358979323846f * (float)(1 << k), is_cos ? 1.57079632679489661923f : 0.0f));
-          }
-          pe[e] = v;
-        }
-#pragma unroll
-        for (int u = 0; u < 6; ++u) store_a8(XA, 128, r, 160 + 8 * u, pack8_bf16(pe + 8 * u));
+        uint32_t pk[16];
+        if (half == 0) pe_words<0>(xc, pk); else pe_words<1>(xc, pk);
+        tmem_st_u16(tl + kM_ColX + 80 + 16 * half, pk);
+        tmem_st_wait();
+        pf.stop(acc_tl);
         hand_over();
       }
       float alpha = 0.f;
       for (int L = 0; L < 9; ++L) {          // L0..L7 (ReLU) and 8 = feature (no activation)
         wait_d();
-        if (L == 5) {                        // x is dead after layer 5: XA <- tok1 for the views layer
-          const uint4* t1 = reinterpret_cast<const uint4*>(a.tok1 + (valid ? i : 0) * kTokLd);
-#pragma unroll
-          for (int u = 0; u < 20; ++u) store_a8(XA, 128, r, 8 * u, valid ? __ldg(t1 + u) : make_uint4(0, 0, 0, 0));
-        }
+        if (L == 5)                          // x is dead after layer 5: XT <- tok1 for the views layer
+          token_to_tmem(a.tok1 + (valid ? i : 0) * kTokLd, valid, half, tl + kM_ColX);
         // the layer kind is warp-uniform: pick a fully specialised epilogue (no per-element branches)
-        if (L == 7) alpha = epi_hidden<true, true>(tl, bias + 256 * 7, w_alpha, HA, r);   // + alpha_linear on fp32 acts
-        else if (L == 8) epi_hidden<false, false>(tl, b_feat, nullptr, HA, r);
-        else epi_hidden<true, false>(tl, bias + 256 * L, nullptr, HA, r);
+        if (L == 7) alpha = epi_hidden<true, true>(tl, half, bias + 256 * 7, w_alpha);   // + alpha_linear on fp32 acts
+        else if (L == 8) epi_hidden<false, false>(tl, half, b_feat, nullptr);
+        else epi_hidden<true, false>(tl, half, bias + 256 * L, nullptr);
         hand_over();
       }
       {
         // ---- views layer epilogue: relu -> rgb_linear on CUDA cores -> raw[pid] = (rgb, alpha)
         wait_d();
         float c0[2] = {0.f, 0.f}, c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
-#pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
-          float t[64];
-          tmem_ld_x32(tl + 64 * cb, *reinterpret_cast<float(*)[32]>(&t[0]));
-          tmem_ld_x32(tl + 64 * cb + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
-          tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(b_views + 64 * cb);
-          const float4* r0 = reinterpret_cast<const float4*>(w_rgb + 64 * cb);
-          const float4* r1 = reinterpret_cast<const float4*>(w_rgb + 128 + 64 * cb);
-          const float4* r2 = reinterpret_cast<const float4*>(w_rgb + 256 + 64 * cb);
+        float t[64];
+        tmem_ld_x32(tl + kM_ColAcc + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
+        tmem_ld_x32(tl + kM_ColAcc + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(b_views + 64 * half);
+        const float4* r0 = reinterpret_cast<const float4*>(w_rgb + 64 * half);
+        const float4* r1 = reinterpret_cast<const float4*>(w_rgb + 128 + 64 * half);
+        const float4* r2 = reinterpret_cast<const float4*>(w_rgb + 256 + 64 * half);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 bb = b4[j], w0 = r0[j], w1 = r1[j], w2 = r2[j];
-            const float v0 = fmaxf(t[4 * j] + bb.x, 0.f), v1 = fmaxf(t[4 * j + 1] + bb.y, 0.f);
-            const float v2 = fmaxf(t[4 * j + 2] + bb.z, 0.f), v3 = fmaxf(t[4 * j + 3] + bb.w, 0.f);
-            c0[0] = fmaf(v0, w0.x, c0[0]); c0[1] = fmaf(v1, w0.y, c0[1]); c0[0] = fmaf(v2, w0.z, c0[0]); c0[1] = fmaf(v3, w0.w, c0[1]);
-            c1[0] = fmaf(v0, w1.x, c1[0]); c1[1] = fmaf(v1, w1.y, c1[1]); c1[0] = fmaf(v2, w1.z, c1[0]); c1[1] = fmaf(v3, w1.w, c1[1]);
-            c2[0] = fmaf(v0, w2.x, c2[0]); c2[1] = fmaf(v1, w2.y, c2[1]); c2[0] = fmaf(v2, w2.z, c2[0]); c2[1] = fmaf(v3, w2.w, c2[1]);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float4 bb = b4[j], w0 = r0[j], w1 = r1[j], w2 = r2[j];
+          const float v0 = fmaxf(t[4 * j] + bb.x, 0.f), v1 = fmaxf(t[4 * j + 1] + bb.y, 0.f);
+          const float v2 = fmaxf(t[4 * j + 2] + bb.z, 0.f), v3 = fmaxf(t[4 * j + 3] + bb.w, 0.f);
+          c0[0] = fmaf(v0, w0.x, c0[0]); c0[1] = fmaf(v1, w0.y, c0[1]); c0[0] = fmaf(v2, w0.z, c0[0]); c0[1] = fmaf(v3, w0.w, c0[1]);
+          c1[0] = fmaf(v0, w1.x, c1[0]); c1[1] = fmaf(v1, w1.y, c1[1]); c1[0] = fmaf(v2, w1.z, c1[0]); c1[1] = fmaf(v3, w1.w, c1[1]);
+          c2[0] = fmaf(v0, w2.x, c2[0]); c2[1] = fmaf(v1, w2.y, c2[1]); c2[0] = fmaf(v2, w2.z, c2[0]); c2[1] = fmaf(v3, w2.w, c2[1]);
         }
-        if (valid)
+        if (half == 1)
+          *reinterpret_cast<float4*>(PART + 4 * r) = make_float4(c0[0] + c0[1], c1[0] + c1[1], c2[0] + c2[1], alpha);
+        epi_bar();
+        if (half == 0 && valid) {
+          const float4 o = *reinterpret_cast<const float4*>(PART + 4 * r);
           reinterpret_cast<float4*>(a.raw)[a.act_pid[i]] =
-              make_float4(c0[0] + c0[1] + b_tail[1], c1[0] + c1[1] + b_tail[2], c2[0] + c2[1] + b_tail[3], alpha + b_tail[0]);
+              make_float4(c0[0] + c0[1] + o.x + b_tail[1], c1[0] + c1[1] + o.y + b_tail[2],
+                          c2[0] + c2[1] + o.z + b_tail[3], alpha + o.w + b_tail[0]);
+        }
+        epi_bar();      // PART is rewritten by the next tile
       }
+      ++n_tiles;
+    }
+    if (pf.on) {
+      atomicAdd(&g_prof[1][0], (unsigned long long)acc_d);
+      atomicAdd(&g_prof[1][1], (unsigned long long)(clock64() - t_begin - acc_d - acc_tl));
+      atomicAdd(&g_prof[1][2], (unsigned long long)acc_tl);
+      atomicAdd(&g_prof[1][7], (unsigned long long)n_tiles);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tm, 256);
+  if (kC > 1) cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc(tm, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -723,7 +825,76 @@ selftest_umma_kernel(const uint16_t* __restrict__ a, const uint8_t* __restrict__
   if (warp == 0) tmem_dealloc(tm, 256);
 }
 
+// Same tile with the A operand written to TENSOR MEMORY by the epilogue threads (tcgen05.st,
+// two bf16 per 32-bit column) and consumed by the TS form of tcgen05.mma.
+__global__ void __launch_bounds__(128, 1)
+selftest_umma_ts_kernel(const uint16_t* __restrict__ a, const uint8_t* __restrict__ b_packed, float* __restrict__ d,
+                        int N, int K, int acol) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int chunks = K / 64;
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  if (tid == 0) { mbar_init(&bar_b, 1); mbar_init(&bar_mma, 1); mbar_fence_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
+  for (int k0 = 0; k0 < K; k0 += 16) {          // 16 bf16 = 8 packed columns per store
+    const uint4 lo = *reinterpret_cast<const uint4*>(a + (size_t)tid * K + k0);
+    const uint4 hi = *reinterpret_cast<const uint4*>(a + (size_t)tid * K + k0 + 8);
+    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    tmem_st_x8(tl + acol + k0 / 2, v);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)chunks * (uint32_t)N * 128u;
+    mbar_arrive_expect_tx(&bar_b, bytes);
+    bulk_g2s(smem, b_packed, bytes, &bar_b);
+    mbar_wait(&bar_b, 0);
+    tc_fence_after();
+    const uint32_t idesc = instr_desc_bf16(N);
+    for (int c = 0; c < chunks; ++c) {
+      const uint32_t b0 = smem_u32(smem + (size_t)c * N * 128);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        mma_bf16_ts(tm, tm + acol + (c * 4 + k4) * 8, smem_desc_sw128(b0 + k4 * 32), idesc, (c | k4) ? 1u : 0u);
+    }
+    mma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c = 0; c < N; c += 16) {
+    float v[16];
+    tmem_ld_x16(tl + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[(size_t)tid * N + c + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
 }  // namespace mps
+
+extern "C" int mpsnerf_selftest_umma_ts(const uint16_t* a, const uint8_t* b_packed, float* d, int N, int K,
+                                        int acol, void* stream) {
+  MPS_REQUIRE(a && b_packed && d);
+  MPS_REQUIRE(acol >= N && acol % 8 == 0 && acol + K / 2 <= 512);
+  MPS_REQUIRE(K >= 64 && K % 64 == 0 && K <= 512 && N >= 16 && N <= 256 && N % 16 == 0);
+  const size_t smem = (size_t)(K / 64) * (size_t)N * 128;
+  MPS_REQUIRE(smem <= 200 * 1024);
+  MPS_CUDA(cudaFuncSetAttribute(mps::selftest_umma_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mps::selftest_umma_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b_packed, d, N, K, acol);
+  MPS_LAUNCH_CHECK();
+  return MPSNERF_OK;
+}
 
 extern "C" int mpsnerf_selftest_umma(const uint16_t* a, const uint8_t* b_packed, float* d, int N, int K,
                                      void* stream) {
@@ -760,30 +931,55 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
   __nv_bfloat16* tok0 = reinterpret_cast<__nv_bfloat16*>(workspace);
   __nv_bfloat16* tok1 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(workspace) + tok_bytes);
 
-  static bool attr_done = false;     // idempotent attribute set; benign if raced
-  if (!attr_done) {
-    MPS_CUDA(cudaFuncSetAttribute(xformer_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT_Smem));
-    MPS_CUDA(cudaFuncSetAttribute(xformer_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT_Smem));
-    MPS_CUDA(cudaFuncSetAttribute(xformer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT_Smem));
-    MPS_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kM_Smem));
-    attr_done = true;
+  // cluster size of the weight multicast: MPSNERF_CLUSTER = 1 | 2 | 4 (default 2)
+  static int cluster = 0;
+  if (cluster == 0) {
+    const char* e = getenv("MPSNERF_CLUSTER");
+    cluster = e ? atoi(e) : 2;
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
   }
-  {
-    TArgs ta{tokens, ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1};
-    const int ppt = 128 / n_views;
-    int64_t tiles = (count + ppt - 1) / ppt;
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    if (n_views == 2) xformer_tc_kernel<2><<<grid, kTcThreads, kT_Smem, st>>>(ta);
-    else if (n_views == 3) xformer_tc_kernel<3><<<grid, kTcThreads, kT_Smem, st>>>(ta);
-    else xformer_tc_kernel<4><<<grid, kTcThreads, kT_Smem, st>>>(ta);
-    MPS_LAUNCH_CHECK();
-  }
-  {
-    MArgs ma{tok0, tok1, xc, count, static_cast<const uint8_t*>(packed), act_pid + first, raw};
-    int64_t tiles = (count + 127) / 128;
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    mlp_tc_kernel<<<grid, kTcThreads, kM_Smem, st>>>(ma);
-    MPS_LAUNCH_CHECK();
-  }
+  static int prof = -1;
+  if (prof < 0) { const char* e = getenv("MPSNERF_TC_PROF"); prof = (e && atoi(e)) ? 1 : 0; }
+  TArgs ta{tokens, ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof};
+  MArgs ma{tok0, tok1, xc, count, static_cast<const uint8_t*>(packed), act_pid + first, raw, prof};
+  const int ppt = 128 / n_views;
+  const int64_t t_tiles = (count + ppt - 1) / ppt, m_tiles = (count + 127) / 128;
+  auto launch = [&](auto kernel, const auto& args, size_t smem_bytes, int64_t tiles, int kc) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (tiles + kc - 1) / kc * kc;                  // whole clusters
+    const int64_t cap = (kNumSMs / kc) * kc;
+    if (ctas > cap) ctas = cap;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)kc;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+  };
+#define MPS_T_CASE(V_, C_) if (n_views == V_ && cluster == C_) MPS_CUDA(launch(xformer_tc_kernel<V_, C_>, ta, kT_Smem, t_tiles, C_));
+  MPS_T_CASE(2, 1) MPS_T_CASE(2, 2) MPS_T_CASE(2, 4)
+  MPS_T_CASE(3, 1) MPS_T_CASE(3, 2) MPS_T_CASE(3, 4)
+  MPS_T_CASE(4, 1) MPS_T_CASE(4, 2) MPS_T_CASE(4, 4)
+#undef MPS_T_CASE
+  if (cluster == 1) MPS_CUDA(launch(mlp_tc_kernel<1>, ma, kM_Smem, m_tiles, 1));
+  if (cluster == 2) MPS_CUDA(launch(mlp_tc_kernel<2>, ma, kM_Smem, m_tiles, 2));
+  if (cluster == 4) MPS_CUDA(launch(mlp_tc_kernel<4>, ma, kM_Smem, m_tiles, 4));
+  return MPSNERF_OK;
+}
+
+// Debug: copy (and clear) the in-kernel cycle counters; out = 16 unsigned 64-bit values (T then M).
+extern "C" int mpsnerf_debug_read_prof(unsigned long long* host_out) {
+  MPS_REQUIRE(host_out != nullptr);
+  MPS_CUDA(cudaMemcpyFromSymbol(host_out, mps::g_prof, sizeof(unsigned long long) * 16));
+  unsigned long long zero[16] = {0};
+  MPS_CUDA(cudaMemcpyToSymbol(mps::g_prof, zero, sizeof(zero)));
   return MPSNERF_OK;
 }

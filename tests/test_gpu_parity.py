@@ -51,6 +51,24 @@ def test_umma_selftest(N, K):
     np.testing.assert_allclose(d.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("N,K,acol", [(256, 256, 256), (192, 192, 352), (160, 64, 432), (128, 128, 432), (256, 384, 256),
+                                      (128, 192, 384), (192, 128, 264), (160, 128, 200)])
+def test_umma_ts_selftest(N, K, acol):
+    """A operand staged in tensor memory (tcgen05.st, 2 bf16 per column) + TS-form tcgen05.mma."""
+    from mpsnerf_b200 import _lib
+    from mpsnerf_b200.engine import pack_kmajor_sw128
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(N * 1000 + K + 7)
+    a = torch.randn(128, K, generator=g).bfloat16().cuda()
+    b = torch.randn(N, K, generator=g).bfloat16().cuda()
+    packed = pack_kmajor_sw128(b.float(), n_pad=N, k_pad=K)
+    d = torch.zeros(128, N, device="cuda")
+    _lib.check(lib.mpsnerf_selftest_umma_ts(_lib.ptr(a), _lib.ptr(packed), _lib.ptr(d), N, K, acol, None), "selftest_ts")
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().T
+    np.testing.assert_allclose(d.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
 def test_knn1_bit_exact_against_oracle():
     from mpsnerf_b200 import _lib, synthetic
     from oracle import oracle as O
