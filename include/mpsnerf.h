@@ -69,6 +69,20 @@ int mpsnerf_abi_version(void);
 /* 0 if device `dev` can run this library (compute capability 10.x), else MPSNERF_EARCH. */
 int mpsnerf_check_device(int dev);
 
+/* ---- K0: per-frame constants on the device ----------------------------------------------
+ * Replaces get_transform_params_torch / batch_rodrigues_torch / get_rigid_transformation_torch
+ * (lib/run_nerf_helpers.py:174-254) and big_pose_params (lib/skinnning_batch.py:193-201), which
+ * the reference runs on the host 4x per chunk.  Inputs are the device tensors of the dataset
+ * dicts (tp = target, sp = source: poses 72, shapes 10, R 9, Th 3; R_all/T_all/K_all of the
+ * input views) and the SMPL tables (v_template (nv,3), shapedirs (nv,3,10), dense J_regressor
+ * (24,nv), parents int32 (24)); fills *out (device). */
+int mpsnerf_frame_prepare(const float* poses_tp, const float* shapes_tp, const float* R_tp, const float* Th_tp,
+                          const float* poses_sp, const float* shapes_sp, const float* R_sp, const float* Th_sp,
+                          const float* cam_R, const float* cam_T, const float* cam_K, int n_views,
+                          int img_w, int img_h, int feat_w, int feat_h, const float* v_template,
+                          const float* shapedirs, const float* J_regressor, const int32_t* parents,
+                          int n_verts, mpsnerf_frame* out, void* stream);
+
 /* ---- nearest-vertex acceleration grid -------------------------------------------------
  * Replaces the brute-force pytorch3d knn_points calls (lib/skinnning_batch.py:214,256,357)
  * with an exact uniform-grid search.  If Th/R are non-null the vertices are first taken to

@@ -33,6 +33,7 @@ SIGNATURES = {
     "mpsnerf_last_error": (ctypes.c_char_p, []),
     "mpsnerf_abi_version": (c_int, []),
     "mpsnerf_check_device": (c_int, [c_int]),
+    "mpsnerf_frame_prepare": (c_int, [c_void_p] * 11 + [c_int] * 5 + [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "mpsnerf_grid_bytes": (c_size_t, [c_int]),
     "mpsnerf_grid_build": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
     "mpsnerf_knn1": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -19,7 +19,6 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .lib.run_nerf_helpers import get_transform_params_torch
 
 GRID_CELL_TARGET = 0.0505      # >= 1.01 * 0.05 m: makes the 27-cell search exact for the mask radius
 GRID_CELL_TEMPLATE = 0.06
@@ -62,6 +61,10 @@ class FrameContext:
     """Device-resident state of one (source, target) pair."""
     __slots__ = ("frame_dev", "grid_tp", "grid_tv", "latent", "img4", "skin_w", "n_views", "keep")
 
+    def frame_host(self):
+        """Host copy of the device-side mpsnerf_frame (tests / debugging; synchronises)."""
+        return _lib.Frame.from_buffer_copy(bytes(self.frame_dev.cpu().numpy()))
+
 
 class RenderEngine:
     def __init__(self, net, precision="fp32", slab=None):
@@ -73,6 +76,7 @@ class RenderEngine:
         self._ws = {}
         self._packed = None
         self._packed_key = None
+        self._smpl_cache = {}
         self.debug = None            # set to a dict to capture per-stage tensors (tests)
         self.timers = None           # set to a dict to record CUDA-event pairs per stage (bench.py)
         self.last_active = 0
@@ -103,6 +107,21 @@ class RenderEngine:
             self._ws[name] = t
         return t
 
+    def _smpl_tables(self, smpl, dev):
+        """Device copies of the SMPL tables of one gender (cached for the life of the engine)."""
+        key = (id(smpl), str(dev))
+        tab = self._smpl_cache.get(key)
+        if tab is None:
+            tab = {
+                "v_template": smpl["v_template"].to(dev).float().contiguous(),
+                "shapedirs": smpl["shapedirs"].to(dev).float().contiguous(),
+                "J_regressor": smpl["J_regressor"].to(dev).float().contiguous(),
+                "parents": smpl["kintree_table"][0].to(dev).to(torch.int32).contiguous(),
+                "weights": smpl["weights"].to(dev).float().contiguous(),
+            }
+            self._smpl_cache[key] = tab
+        return tab
+
     def _weights_fp32(self):
         sd = dict(self.net.named_parameters())
         tensors = [sd[k].detach() for k in DENSE_FP32_ORDER]
@@ -123,61 +142,30 @@ class RenderEngine:
         lib = self.lib
         V = sp["img_all"].shape[0]
         assert 2 <= V <= _lib.MAX_VIEWS
-        # one D2H of the small per-frame parameters
-        flat = torch.cat([tp["params"]["poses"].reshape(-1), tp["params"]["shapes"].reshape(-1),
-                          tp["params"]["R"].reshape(-1), tp["params"]["Th"].reshape(-1),
-                          sp["params"]["poses"].reshape(-1), sp["params"]["shapes"].reshape(-1),
-                          sp["params"]["R"].reshape(-1), sp["params"]["Th"].reshape(-1),
-                          sp["R_all"].reshape(-1), sp["T_all"].reshape(-1), sp["K_all"].reshape(-1)]).float().cpu()
-        o = 0
-
-        def take(n):
-            nonlocal o
-            v = flat[o:o + n]
-            o += n
-            return v
-
-        def params():
-            return {"poses": take(72).reshape(1, 72), "shapes": take(10).reshape(1, 10), "R": take(9).reshape(3, 3),
-                    "Th": take(3).reshape(1, 3)}
-
-        tpp, spp = params(), params()
-        cam_R, cam_T, cam_K = take(9 * V), take(3 * V), take(9 * V)
-        big = torch.zeros(1, 72)                                     # lib/skinnning_batch.py:193-201
-        big[0, 5], big[0, 8], big[0, 23], big[0, 26] = np.pi / 4, -np.pi / 4, -np.pi / 6, np.pi / 6
-
-        def A12(poses, shapes):
-            A = get_transform_params_torch(smpl, {"poses": poses, "shapes": shapes, "R": None, "Th": None})[0]
-            return A[:, :3, :].reshape(-1).numpy()
-
-        fr = _lib.Frame()
-        fr.Th_tp[:] = tpp["Th"].reshape(-1).tolist()
-        fr.R_tp[:] = tpp["R"].reshape(-1).tolist()
-        fr.Rinv_sp[:] = torch.inverse(spp["R"]).reshape(-1).tolist()
-        fr.Th_sp[:] = spp["Th"].reshape(-1).tolist()
-        fr.A_tp[:] = A12(tpp["poses"], tpp["shapes"]).tolist()
-        fr.A_big_tp[:] = A12(big, tpp["shapes"]).tolist()
-        fr.A_big_sp[:] = A12(big, spp["shapes"]).tolist()
-        fr.A_sp[:] = A12(spp["poses"], spp["shapes"]).tolist()
-        fr.cam_R[:9 * V] = cam_R.tolist()
-        fr.cam_T[:3 * V] = cam_T.tolist()
-        fr.cam_K[:9 * V] = cam_K.tolist()
         H, W = sp["img_all"].shape[-2:]
-        fr.n_views, fr.img_w, fr.img_h = V, W, H
-
         ctx = FrameContext()
         ctx.n_views = V
         # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
         # (cuDNN convolutions default to TF32; the fp32 precision mode keeps true fp32 end to end)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=(self.precision != "fp32")):
             latent = self.net.encoder_2d(sp["img_all"])
-        fr.feat_w, fr.feat_h = latent.shape[-1], latent.shape[-2]
         ctx.latent = latent.permute(0, 2, 3, 1).contiguous().float()
         ctx.img4 = F.pad(sp["img_all"].permute(0, 2, 3, 1), (0, 1)).contiguous().float()
-        host = torch.frombuffer(bytearray(bytes(fr)), dtype=torch.uint8)
-        ctx.frame_dev = host.to(dev)
-        ctx.skin_w = smpl["weights"].to(dev).float().contiguous()
-        ctx.keep = (fr,)
+        # K0: LBS transforms (target / big / source pose), cameras -> mpsnerf_frame, all on the device
+        tab = self._smpl_tables(smpl, dev)
+        ctx.skin_w = tab["weights"]
+        ctx.frame_dev = torch.empty(ctypes.sizeof(_lib.Frame), dtype=torch.uint8, device=dev)
+        f32 = lambda t: t.reshape(-1).float().contiguous()
+        keep = [f32(tp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
+               [f32(sp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
+               [f32(sp["R_all"]), f32(sp["T_all"]), f32(sp["K_all"])]
+        _lib.check(lib.mpsnerf_frame_prepare(*[_lib.ptr(t) for t in keep], V, W, H, latent.shape[-1], latent.shape[-2],
+                                             _lib.ptr(tab["v_template"]), _lib.ptr(tab["shapedirs"]),
+                                             _lib.ptr(tab["J_regressor"]), _lib.ptr(tab["parents"]),
+                                             tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
+                   "frame_prepare")
+        _lib.count_launches(1)
+        ctx.keep = keep
 
         nv = tp["vertices"].shape[0]
         gb = lib.mpsnerf_grid_bytes(nv)

@@ -122,7 +122,7 @@ def test_composite_against_oracle():
 def _engine_consts(ctx, oc):
     """Oracle frame constants with the per-frame matrices replaced by the ones the engine
     uploaded, so that the bit-exact stages are compared on identical inputs."""
-    fr = ctx.keep[0]
+    fr = ctx.frame_host()
     c = dict(oc)
     f32 = lambda a, *s: np.array(list(a), dtype=np.float32).reshape(*s)
     c.update(A_tp=f32(fr.A_tp, 24, 12), A_big_tp=f32(fr.A_big_tp, 24, 12), A_big_sp=f32(fr.A_big_sp, 24, 12),
