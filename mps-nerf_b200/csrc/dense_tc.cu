@@ -42,7 +42,7 @@ constexpr int kTokLd = 160;   // bf16 row stride of tok0 / tok1 handed from T to
 // Optional in-kernel cycle accounting (MPSNERF_TC_PROF=1): per kernel 8 counters summed over CTAs:
 // 0 epilogue wait-for-MMA, 1 epilogue work, 2 tile load, 3 MMA wait-for-A, 4 MMA wait-for-weights,
 // 5 MMA thread total, 6 producer wait-for-free-slot, 7 tiles.  Read with mpsnerf_debug_read_prof().
-__device__ unsigned long long g_prof[2][8];
+__device__ unsigned long long g_prof[2][16];   // [8..15]: T epilogue sections, see tools/step.py
 struct Prof {
   bool on;
   long long t;
@@ -55,20 +55,29 @@ struct Pipe {            // barriers of one CTA (in dynamic smem)
   uint64_t empty[8];
   uint64_t a_bar;
   uint64_t d_bar;
+  uint64_t r_bar;       // T kernel: "scratch accumulator R has been copied out" (early release)
   uint32_t tmem_base;
   uint32_t pad;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
-  // 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7)
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  // 0.5 x (1 + erf(x / sqrt 2)) with erf(z) = z * P(z^2) on |z| <= 3 (degree-9 Chebyshev fit, max
+  // |err| 1.6e-5 in fp32; saturates to +-0.99998 beyond).  Deliberately free of MUFU ops (ex2 / rcp):
+  // the special-function unit was the bottleneck of this epilogue (2 MUFU per element).
+  const float z = fminf(fmaxf(x * 0.70710678118654752440f, -3.0f), 3.0f);
+  const float w = z * z;
+  float p = -4.6617889859e-09f;
+  p = fmaf(p, w, 2.3821795289e-07f);
+  p = fmaf(p, w, -5.4625094310e-06f);
+  p = fmaf(p, w, 7.5274732228e-05f);
+  p = fmaf(p, w, -7.0841461755e-04f);
+  p = fmaf(p, w, 4.9218977801e-03f);
+  p = fmaf(p, w, -2.6500707362e-02f);
+  p = fmaf(p, w, 1.1261424783e-01f);
+  p = fmaf(p, w, -3.7607604539e-01f);
+  p = fmaf(p, w, 1.1283780006e+00f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, z * p, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -139,12 +148,12 @@ struct Consumer {            // used by the single MMA thread
 //   OT [432,496)  attention output of one head (K = 64, 32 cols) or GELU(FF hidden) (K = 128, 64 cols)
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kT_ColX = 0, kT_ColR = 160, kT_ColY = 352, kT_ColO = 432;
-constexpr uint32_t kT_KX = 0;                      // k of the current head, fp16 [128][64], unit-swizzled
-constexpr uint32_t kT_VX = kT_KX + 16384;
+constexpr uint32_t kT_KX = 0;                      // k of the current head, fp32 [128][64], rows of 256 B, unit-swizzled
+constexpr uint32_t kT_VX = kT_KX + 32768;          // v of the current head, fp16 [128][64], rows of 128 B, unit-swizzled
 constexpr uint32_t kT_PD = kT_VX + 16384;          // partial q.k dots  float[2][128][4]
 constexpr uint32_t kT_LS = kT_PD + 4096;           // LayerNorm partial sums float[2][2][128]
-constexpr uint32_t kT_RING = kT_LS + 2048;         // 1024-aligned: 16384*2 + 4096 + 2048 = 38912 = 38 * 1024
-constexpr int kT_Slots = 7;
+constexpr uint32_t kT_RING = kT_LS + 2048;         // 1024-aligned: 32768 + 16384 + 4096 + 2048 = 55296 = 54 * 1024
+constexpr int kT_Slots = 6;
 constexpr uint32_t kT_SlotBytes = kQkvChunk;
 constexpr uint32_t kT_FP = kT_RING + kT_Slots * kT_SlotBytes;
 constexpr uint32_t kT_PIPE = kT_FP + ((kTFloats * 4 + 15) / 16) * 16;
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
     for (int i = 0; i < kT_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], kC); }
     mbar_init(&pipe->a_bar, kEpiThreads);
     mbar_init(&pipe->d_bar, 1);
+    mbar_init(&pipe->r_bar, kEpiThreads);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
@@ -254,9 +264,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
       for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {   // cluster-uniform trip count
         for (int l = 0; l < 2; ++l) {
           const uint8_t* src = a.blob + (size_t)l * kTLayerBytes;
-          for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);
-          for (int h = 1; h < 4; ++h) { P.push(src, kWoChunk); for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk); }
-          P.push(src, kWoChunk);
+          for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);                                   // qkv_0
+          for (int h = 0; h < 3; ++h) { for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk); P.push(src, kWoChunk); }   // qkv_{h+1}, Wo_h
+          P.push(src, kWoChunk);                                                                 // Wo_3
           for (int c = 0; c < 3; ++c) P.push(src, kW1Chunk);
           for (int c = 0; c < 2; ++c) P.push(src, kW2Chunk);
         }
@@ -268,6 +278,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
     if (lane == 0) {
       Consumer<kT_Slots, kT_SlotBytes, kC> Cn{pipe, smem_u32(smem + kT_RING)};
       Cn.pf = Prof{a.prof != 0, 0};
+      uint32_t rr = 0;
       const long long t_begin = clock64();
       // A (TMEM, `ksteps` K=16 steps starting at column acol) x weight chunks with N rows -> D column dcol
       auto gemm = [&](uint32_t dcol, uint32_t acol, int ksteps, int N, bool accumulate) {
@@ -286,13 +297,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
       for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
         for (int l = 0; l < 2; ++l) {
           Cn.wait_a(); gemm(kT_ColR, kT_ColY, 10, 192, false); Cn.done();           // q|k|v of head 0
-          for (int h = 1; h < 4; ++h) {
+          for (int h = 0; h < 4; ++h) {
+            if (h < 3) {                                                             // R copied out by the epilogue:
+              mbar_wait(&pipe->r_bar, rr & 1); ++rr; tc_fence_after();               // q|k|v of head h+1 overlaps the
+              gemm(kT_ColR, kT_ColY, 10, 192, false);                                // attention math of head h
+            }
             Cn.wait_a();
-            gemm(kT_ColX, kT_ColO, 4, 160, true);                                    // x += o_{h-1} Wo_{h-1}^T
-            gemm(kT_ColR, kT_ColY, 10, 192, false);                                  // q|k|v of head h
+            gemm(kT_ColX, kT_ColO, 4, 160, true);                                    // x += o_h Wo_h^T
             Cn.done();
           }
-          Cn.wait_a(); gemm(kT_ColX, kT_ColO, 4, 160, true); Cn.done();
           Cn.wait_a(); gemm(kT_ColR, kT_ColY, 10, 128, false); Cn.done();            // FF hidden
           Cn.wait_a(); gemm(kT_ColX, kT_ColO, 8, 160, true); Cn.done();              // x += gelu(.) W2^T
         }
@@ -314,6 +327,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
     uint32_t g = 0;
     Prof pf{a.prof != 0 && tid == 0, 0};
     long long acc_d = 0, acc_tl = 0, n_tiles = 0;
+    long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // publish, bar1, dots, bar2, softmax+o, LN2, GELU, LN1/final
     const long long t_begin = clock64();
     auto hand_over = [&]() { tc_fence_before(); mbar_arrive(&pipe->a_bar); };
     auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar, g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
@@ -355,45 +369,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
         const float* fp = FP + l * kTLayerFloats;   // ln1_g ln1_b pend_in ln2_g ln2_b pend_mid b1
         for (int h = 0; h < 4; ++h) {
           wait_d();
+          pf.start();
           // ---- attention of head h (lib/transformer.py:59-71): R = [q | k | v], 64 columns each.
-          // half 0 publishes k, half 1 publishes v (fp16, unit-swizzled rows of 128 B)
+          // half 0 publishes k as fp32, half 1 publishes v as fp16 (unit-swizzled rows)
           {
             float t[64];
             tmem_ld_x32(tl + kT_ColR + 64 + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
             tmem_ld_x32(tl + kT_ColR + 64 + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
             tmem_ld_wait();
-            uint8_t* dst = (half == 0 ? KX : VX) + r * 128;
+            if (half == 0) {
+              uint8_t* dst = KX + r * 256;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint4 pk = make_uint4(pack_h2(t[8 * u], t[8 * u + 1]), pack_h2(t[8 * u + 2], t[8 * u + 3]),
-                                          pack_h2(t[8 * u + 4], t[8 * u + 5]), pack_h2(t[8 * u + 6], t[8 * u + 7]));
-              *reinterpret_cast<uint4*>(dst + ((u ^ (r & 7)) << 4)) = pk;
+              for (int u = 0; u < 16; ++u)
+                *reinterpret_cast<float4*>(dst + ((u ^ (r & 15)) << 4)) = make_float4(t[4 * u], t[4 * u + 1], t[4 * u + 2], t[4 * u + 3]);
+            } else {
+              uint8_t* dst = VX + r * 128;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint4 pk = make_uint4(pack_h2(t[8 * u], t[8 * u + 1]), pack_h2(t[8 * u + 2], t[8 * u + 3]),
+                                            pack_h2(t[8 * u + 4], t[8 * u + 5]), pack_h2(t[8 * u + 6], t[8 * u + 7]));
+                *reinterpret_cast<uint4*>(dst + ((u ^ (r & 7)) << 4)) = pk;
+              }
             }
           }
           float q[32];
           tmem_ld_x32(tl + kT_ColR + 32 * half, q);
           tmem_ld_wait();
+          if (h < 3) { tc_fence_before(); mbar_arrive(&pipe->r_bar); }   // R is free: the next head's q|k|v may land
+          pf.stop(sec[0]);
           epi_bar();
-          // partial dots over this thread's 32 of the 64 head dims
+          pf.stop(sec[1]);
+          // partial dots over this thread's 32 of the 64 head dims (fp32, no conversions)
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const int rj = p0 + j;
-            const uint8_t* src = KX + rj * 128;
+            const uint8_t* src = KX + rj * 256;
+            float4 kk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)      // all loads of the row first: one exposed smem latency per row
+              kk[u] = *reinterpret_cast<const float4*>(src + (((8 * half + u) ^ (rj & 15)) << 4));
             float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(src + (((4 * half + u) ^ (rj & 7)) << 4));
-              const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h2[i]);
-                d[i] = fmaf(q[8 * u + 2 * i], f.x, d[i]);
-                d[i] = fmaf(q[8 * u + 2 * i + 1], f.y, d[i]);
-              }
+            for (int u = 0; u < 8; ++u) {
+              d[0] = fmaf(q[4 * u], kk[u].x, d[0]); d[1] = fmaf(q[4 * u + 1], kk[u].y, d[1]);
+              d[2] = fmaf(q[4 * u + 2], kk[u].z, d[2]); d[3] = fmaf(q[4 * u + 3], kk[u].w, d[3]);
             }
             PD[(half * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
           }
+          pf.stop(sec[2]);
           epi_bar();
+          pf.stop(sec[3]);
           float w[V];
           float mx = -1e30f;
 #pragma unroll
@@ -405,44 +430,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
 #pragma unroll
           for (int j = 0; j < V; ++j) { w[j] = __expf(w[j] - mx); den += w[j]; }
           const float inv = 1.0f / den;
-          float o[32];
+          // o = sum_j softmax_j * v_j over this thread's 32 dims, accumulated as half2 (3 terms;
+          // the result is rounded to bf16 for the out-projection anyway)
+          __half2 oh[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0.f;
+          for (int i = 0; i < 16; ++i) oh[i] = __float2half2_rn(0.f);
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const int rj = p0 + j;
-            const float wj = w[j] * inv;
+            const __half2 wj = __float2half2_rn(w[j] * inv);
             const uint8_t* src = VX + rj * 128;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(src + (((4 * half + u) ^ (rj & 7)) << 4));
-              const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+              const uint4 pkv = *reinterpret_cast<const uint4*>(src + (((4 * half + u) ^ (rj & 7)) << 4));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&pkv);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h2[i]);
-                o[8 * u + 2 * i] = fmaf(wj, f.x, o[8 * u + 2 * i]);
-                o[8 * u + 2 * i + 1] = fmaf(wj, f.y, o[8 * u + 2 * i + 1]);
-              }
+              for (int i = 0; i < 4; ++i) oh[4 * u + i] = __hfma2(wj, h2[i], oh[4 * u + i]);
             }
           }
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+          for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(oh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
           tmem_st_u16(tl + kT_ColO + 16 * half, pk);
           tmem_st_wait();
+          pf.stop(sec[4]);
           hand_over();
         }
         {
           // ---- x (+ deferred biases) -> LN2 -> YT
           wait_d();
+          pf.start();
           float x[80];
           load_x80(tl + kT_ColX + 80 * half, x);
           ln_to_tmem(x, fp + 800, fp + 480, fp + 640, LS, r, half, tl);
+          pf.stop(sec[5]);
           hand_over();
         }
         {
           // ---- FF hidden: GELU(acc + b1) -> bf16 operand (K = 128 -> 64 packed columns)
           wait_d();
+          pf.start();
           float t[64];
           tmem_ld_x32(tl + kT_ColR + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
           tmem_ld_x32(tl + kT_ColR + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
@@ -458,15 +485,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
           tmem_st_u16(tl + kT_ColO + 32 * half, pk);
           tmem_st_u16(tl + kT_ColO + 32 * half + 16, pk + 16);
           tmem_st_wait();
+          pf.stop(sec[6]);
           hand_over();
         }
         {
           wait_d();
+          pf.start();
           float x[80];
           load_x80(tl + kT_ColX + 80 * half, x);
           if (l == 0) {
             const float* f1 = FP + kTLayerFloats;        // layer 1: LN1 on x + pend_in
             ln_to_tmem(x, f1 + 320, f1, f1 + 160, LS, r, half, tl);
+            pf.stop(sec[7]);
             hand_over();
           } else if (valid && tok < 2) {
             // ---- output tokens 0 (density branch) and 1 (colour branch), lib/skinnning_batch.py:441-442
@@ -488,6 +518,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
       atomicAdd(&g_prof[0][1], (unsigned long long)(clock64() - t_begin - acc_d - acc_tl));
       atomicAdd(&g_prof[0][2], (unsigned long long)acc_tl);
       atomicAdd(&g_prof[0][7], (unsigned long long)n_tiles);
+      for (int k = 0; k < 8; ++k) atomicAdd(&g_prof[0][8 + k], (unsigned long long)sec[k]);
     }
   }
   tc_fence_before();
@@ -978,8 +1009,8 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
 // Debug: copy (and clear) the in-kernel cycle counters; out = 16 unsigned 64-bit values (T then M).
 extern "C" int mpsnerf_debug_read_prof(unsigned long long* host_out) {
   MPS_REQUIRE(host_out != nullptr);
-  MPS_CUDA(cudaMemcpyFromSymbol(host_out, mps::g_prof, sizeof(unsigned long long) * 16));
-  unsigned long long zero[16] = {0};
+  MPS_CUDA(cudaMemcpyFromSymbol(host_out, mps::g_prof, sizeof(unsigned long long) * 32));
+  unsigned long long zero[32] = {0};
   MPS_CUDA(cudaMemcpyToSymbol(mps::g_prof, zero, sizeof(zero)));
   return MPSNERF_OK;
 }

@@ -4,7 +4,7 @@ Layout (bytes; every weight tile is K-major bf16 in SWIZZLE_128B chunks, see
 ``engine.pack_kmajor_sw128``), in the exact order the kernels stream it:
 
   transformer, per layer l (466 944 B):
-      qkv_0[3 chunks x 192 rows]; then for h = 1..3: Wo_{h-1}[1 x 160], qkv_h[3 x 192];
+      qkv_0[3 chunks x 192 rows]; then for h = 0..2: qkv_{h+1}[3 x 192], Wo_h[1 x 160];
       Wo_3[1 x 160]; W1[3 x 128]; W2[2 x 160]
       qkv_h rows = (q_h | k_h | v_h) = to_qkv rows 64h.., 256+64h.., 512+64h..   (K = 155 -> 192)
   MLP (1 425 408 B):
@@ -53,9 +53,9 @@ def pack_weights_bf16(net, device=None):
                           wqkv[512 + 64 * h:512 + 64 * h + 64]], 0) for h in range(4)]
         out = [wo[:, 64 * h:64 * h + 64] for h in range(4)]
         parts.append(pack_kmajor_sw128(qkv[0], 192, 192))
-        for h in range(1, 4):
-            parts.append(pack_kmajor_sw128(out[h - 1], 160, 64))
-            parts.append(pack_kmajor_sw128(qkv[h], 192, 192))
+        for h in range(3):            # q|k|v of head h+1 is streamed before Wo_h (its GEMM is issued first)
+            parts.append(pack_kmajor_sw128(qkv[h + 1], 192, 192))
+            parts.append(pack_kmajor_sw128(out[h], 160, 64))
         parts.append(pack_kmajor_sw128(out[3], 160, 64))
         parts.append(pack_kmajor_sw128(w1, 128, 192))
         parts.append(pack_kmajor_sw128(w2, 160, 128))

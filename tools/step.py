@@ -30,13 +30,16 @@ def main():
     if os.environ.get("MPSNERF_TC_PROF"):
         import ctypes
         from mpsnerf_b200 import _lib
-        buf = (ctypes.c_ulonglong * 16)()
+        buf = (ctypes.c_ulonglong * 32)()
         _lib.check(_lib.load().mpsnerf_debug_read_prof(buf), "read_prof")
         names = ["epi_wait_mma", "epi_work", "tile_load", "mma_wait_A", "mma_wait_W", "mma_total", "prod_wait_slot", "tiles"]
         for k, kn in enumerate(("T", "M")):
-            v = [buf[8 * k + i] for i in range(8)]
+            v = [buf[16 * k + i] for i in range(16)]
             tiles = max(v[7], 1)
             print(kn, "tiles(cta0-thread0 sum)", v[7], {n: round(x / tiles) for n, x in zip(names[:7], v[:7])}, "cycles/tile")
+            if k == 0:
+                sn = ["publish", "bar1", "dots", "bar2", "softmax_o", "LN2", "GELU", "LN1"]
+                print("  T sections", {n: round(x / tiles) for n, x in zip(sn, v[8:16])})
 
 
 if __name__ == "__main__":
