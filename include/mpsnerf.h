@@ -181,6 +181,8 @@ int mpsnerf_selftest_umma_ts(const uint16_t* a, const uint8_t* b_packed, float* 
 /* Debug: with MPSNERF_TC_PROF=1 the tensor-core kernels accumulate per-role cycle counters
  * (see csrc/dense_tc.cu); this copies the 2 x 16 counters to the host and clears them. */
 int mpsnerf_debug_read_prof(unsigned long long* host_out);
+/* Debug: copy the 512-entry event trace recorded with MPSNERF_TC_PROF=2 (tag << 48 | clock). */
+int mpsnerf_debug_read_trace(unsigned long long* host_out);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,7 @@ SIGNATURES = {
     "mpsnerf_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mpsnerf_selftest_umma_ts": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mpsnerf_debug_read_prof": (c_int, [c_void_p]),
+    "mpsnerf_debug_read_trace": (c_int, [c_void_p]),
 }
 
 _lib = None

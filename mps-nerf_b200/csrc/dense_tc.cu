@@ -17,6 +17,8 @@
 // d_bar: "accumulator ready", tcgen05.commit).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -31,11 +33,11 @@ constexpr int kProdWarp = 8, kMmaWarp = 9;
 constexpr uint32_t kQkvChunk = 192 * 128, kWoChunk = 160 * 128, kW1Chunk = 128 * 128, kW2Chunk = 160 * 128;
 constexpr uint32_t kTLayerBytes = 12 * kQkvChunk + 4 * kWoChunk + 3 * kW1Chunk + 2 * kW2Chunk;
 constexpr uint32_t kTBytes = 2 * kTLayerBytes;
-constexpr uint32_t kMBytes = 40 * 32768 + 7 * 16384;
+constexpr uint32_t kMBytes = 44 * 32768;
 constexpr uint32_t kFloatOff = kTBytes + kMBytes;
 constexpr int kTLayerFloats = 1088, kTFloats = 2 * kTLayerFloats + 160, kMFloats = 8 * 256 + 256 + 256 + 128 + 384 + 4;
 constexpr size_t kBlobBytes = (size_t)kFloatOff + 4 * (size_t)(kTFloats + kMFloats);
-static_assert(kTLayerBytes == 466944 && kMBytes == 1425408, "blob layout drifted from pack.py");
+static_assert(kTLayerBytes == 466944 && kMBytes == 1441792, "blob layout drifted from pack.py");
 
 constexpr int kTokLd = 160;   // bf16 row stride of tok0 / tok1 handed from T to M
 
@@ -43,6 +45,14 @@ constexpr int kTokLd = 160;   // bf16 row stride of tok0 / tok1 handed from T to
 // 0 epilogue wait-for-MMA, 1 epilogue work, 2 tile load, 3 MMA wait-for-A, 4 MMA wait-for-weights,
 // 5 MMA thread total, 6 producer wait-for-free-slot, 7 tiles.  Read with mpsnerf_debug_read_prof().
 __device__ unsigned long long g_prof[2][16];   // [8..15]: T epilogue sections, see tools/step.py
+// Optional event trace of CTA 0's second tile (MPSNERF_TC_PROF=2): [0,256) MMA thread, [256,512) epilogue thread 0;
+// each entry = (tag << 48) | (clock64 & 0xffffffffffff).  Read with mpsnerf_debug_read_trace().
+__device__ unsigned long long g_trace[512];
+struct Trace {
+  bool on; int n; int base;
+  __device__ __forceinline__ void ev(int tag) { if (on && n < 256) { g_trace[base + n] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xffffffffffffull); ++n; } }
+};
+
 struct Prof {
   bool on;
   long long t;
@@ -51,10 +61,11 @@ struct Prof {
 };
 
 struct Pipe {            // barriers of one CTA (in dynamic smem)
-  uint64_t full[8];
-  uint64_t empty[8];
-  uint64_t a_bar;
-  uint64_t d_bar;
+  uint64_t full[16];
+  uint64_t empty[16];
+  uint64_t a_bar[2];    // "A operand ready" (M kernel: one per K-half)
+  uint64_t d_bar[2];    // "accumulator ready" (M kernel: one per N-half)
+  uint64_t k_bar;       // M kernel: "[h1: K0] done, HT K-half 0 may be overwritten"
   uint64_t r_bar;       // T kernel: "scratch accumulator R has been copied out" (early release)
   uint32_t tmem_base;
   uint32_t pad;
@@ -121,8 +132,8 @@ struct Consumer {            // used by the single MMA thread
   uint32_t it = 0, g = 0;
   Prof pf;
   long long acc_a = 0, acc_w = 0;
-  __device__ __forceinline__ void wait_a() { pf.start(); mbar_wait(&pipe->a_bar, g & 1); pf.stop(acc_a); tc_fence_after(); }
-  __device__ __forceinline__ void done() { mma_commit(&pipe->d_bar); ++g; }
+  __device__ __forceinline__ void wait_a() { pf.start(); mbar_wait(&pipe->a_bar[0], g & 1); pf.stop(acc_a); tc_fence_after(); }
+  __device__ __forceinline__ void done() { mma_commit(&pipe->d_bar[0]); ++g; }
   __device__ __forceinline__ uint32_t slot_wait() {
     const uint32_t slot = it % kSlots;
     pf.start();
@@ -136,6 +147,56 @@ struct Consumer {            // used by the single MMA thread
     else mma_commit_mc(&pipe->empty[it % kSlots], (uint16_t)((1u << kC) - 1u));
     ++it;
   }
+};
+
+// Warp-converged versions (whole warp runs the control flow, one elected lane issues):
+template <int kSlots, uint32_t kSlotBytes, int kC>
+struct RingProducer {
+  Pipe* pipe;
+  uint8_t* ring;
+  uint32_t crank;
+  uint32_t slot = 0, phase = 0;
+  Prof pf{false, 0};
+  long long acc_e = 0;
+  __device__ __forceinline__ void push(const uint8_t*& src, uint32_t bytes) {
+    pf.start();
+    mbar_wait(&pipe->empty[slot], phase ^ 1);
+    pf.stop(acc_e);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&pipe->full[slot], bytes);          // the whole chunk lands here (kC slices)
+      if (kC == 1) {
+        bulk_g2s(ring + slot * kSlotBytes, src, bytes, &pipe->full[slot]);
+      } else {
+        const uint32_t slice = bytes / kC;
+        bulk_g2s_mc(ring + slot * kSlotBytes + crank * slice, src + crank * slice, slice, &pipe->full[slot],
+                    (uint16_t)((1u << kC) - 1u));
+      }
+    }
+    __syncwarp();
+    src += bytes;
+    if (++slot == kSlots) { slot = 0; phase ^= 1; }
+  }
+};
+
+template <int kSlots, uint32_t kSlotBytes, int kC>
+struct RingConsumer {
+  Pipe* pipe;
+  uint32_t ring_addr;
+  uint32_t slot = 0, phase = 0;
+  Prof pf{false, 0};
+  long long acc_w = 0;
+  __device__ __forceinline__ uint32_t acquire() {       // all lanes
+    pf.start();
+    mbar_wait(&pipe->full[slot], phase);
+    pf.stop(acc_w);
+    tc_fence_after();
+    return ring_addr + slot * kSlotBytes;
+  }
+  __device__ __forceinline__ void release_elected() {   // elected lane, after its MMAs
+    if (kC == 1) mma_commit(&pipe->empty[slot]);
+    else mma_commit_mc(&pipe->empty[slot], (uint16_t)((1u << kC) - 1u));
+  }
+  __device__ __forceinline__ void advance() { if (++slot == kSlots) { slot = 0; phase ^= 1; } }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -240,8 +301,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
 
   if (tid == 0) {
     for (int i = 0; i < kT_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], kC); }
-    mbar_init(&pipe->a_bar, kEpiThreads);
-    mbar_init(&pipe->d_bar, 1);
+    mbar_init(&pipe->a_bar[0], kEpiThreads);
+    mbar_init(&pipe->d_bar[0], 1);
     mbar_init(&pipe->r_bar, kEpiThreads);
     mbar_fence_init();
   }
@@ -329,8 +390,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
     long long acc_d = 0, acc_tl = 0, n_tiles = 0;
     long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // publish, bar1, dots, bar2, softmax+o, LN2, GELU, LN1/final
     const long long t_begin = clock64();
-    auto hand_over = [&]() { tc_fence_before(); mbar_arrive(&pipe->a_bar); };
-    auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar, g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
+    auto hand_over = [&]() { tc_fence_before(); mbar_arrive(&pipe->a_bar[0]); };
+    auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar[0], g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
     constexpr int rows = ppt * V;
     const int p0 = (r < rows) ? (r / V) * V : 0;      // first row of this row's point (attention partners)
 
@@ -529,21 +590,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
 
 // ------------------------------------------------------------------------------------------
 // M: canonical NeRF MLP.  Tile = 128 points.  TMEM columns:
-//   ACC [0,256)    accumulator
-//   HT  [256,384)  hidden activations, bf16 x2 per column (K = 256)
-//   XT  [384,496)  x = [tok0 155 | 0 x5 | PE6(xc) 39 | 0 x25] (K = 224, 14 K-steps);
-//                  reused for tok1 (K = 160) after layer 5
-// Shared memory holds only the weight ring (6 x 32 KB) and the fp32 parameter vectors.
+//   ACC0 [0,128), ACC1 [128,256)   the two N-halves of the layer output (fp32)
+//   HT   [256,384)  hidden activations, bf16 x2 per column (K = 256); K-half j = columns 256 + 64 j ..
+//   XT   [384,496)  x = [tok0 155 | 0 x5 | PE6(xc) 39 | 0 x25] (K = 224, 14 K-steps);
+//                   reused for tok1 (K = 160) after layer 5
+// Software pipeline inside one tile (all MMAs are M = 128, N = 128, K = 16):
+//   a layer is issued as  [h0: K0 K1] commit d_bar0  [h1: K0] commit k_bar  [h1: K1] commit d_bar1
+//   the epilogue turns half 0 (e0) into K-half 0 of the next layer's operand while the tensor pipe
+//   computes half 1, and half 1 (e1) while it already runs the next layer's [h0: K0]:
+//     [h0': K0] needs e0 (a_bar0), [h0': K1] needs e1 (a_bar1); e0 may overwrite HT K-half 0 only
+//     after [h1: K0] has read it (k_bar).
+// The next tile's x is prefetched into registers and stored to XT inside the views epilogue,
+// before the colour math, so the tensor pipe restarts while the tile's output is still being written.
+// Shared memory holds only the weight ring (12 x 16 KB) and the fp32 parameter vectors.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kM_ColAcc = 0, kM_ColH = 256, kM_ColX = 384;
 constexpr uint32_t kM_RING = 0;
-constexpr int kM_Slots = 6;
-constexpr uint32_t kM_SlotBytes = 32768;
+constexpr int kM_Slots = 3;
+static_assert(kM_Slots <= 16 && kT_Slots <= 16, "Pipe holds 16 ring barriers");
+constexpr uint32_t kM_SlotBytes = 65536;         // one half-layer: 128 weight rows x K = 256 (4 chunks, 16 MMAs)
+constexpr int kM_SlotsPerTile = 22;
 constexpr uint32_t kM_FP = kM_RING + kM_Slots * kM_SlotBytes;
-constexpr uint32_t kM_PART = kM_FP + ((kMFloats * 4 + 15) / 16) * 16;   // float[128][4]: alpha / rgb partials of half 1
-constexpr uint32_t kM_PIPE = kM_PART + 128 * 16;
+constexpr uint32_t kM_PART = kM_FP + ((kMFloats * 4 + 15) / 16) * 16;   // float4[3][128]: alpha / rgb partials of quarters 1..3
+constexpr uint32_t kM_PIPE = kM_PART + 3 * 128 * 16;
 constexpr uint32_t kM_Smem = kM_PIPE + sizeof(Pipe);
 static_assert(kM_Smem <= 232448 - 1024, "M kernel shared memory over budget");
+static_assert(kM_SlotsPerTile * kM_SlotBytes == kMBytes, "M weight stream drifted from pack.py");
 
 struct MArgs {
   const __nv_bfloat16* tok0;
@@ -556,81 +628,121 @@ struct MArgs {
   int prof;
 };
 
-// Hidden-layer epilogue of one thread: 128 accumulator columns (its half of the row) ->
-// (+bias, ReLU) -> bf16 x2 -> HT.  Everything compile-time so the inner loops are branch-free.
-// Returns this half's sum_j act_j * w_alpha_j when kAlpha.
-template <bool kRelu, bool kAlpha>
-__device__ __forceinline__ float epi_hidden(uint32_t tl, int half, const float* __restrict__ b,
-                                            const float* __restrict__ w_alpha) {
-  float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int cb = 0; cb < 2; ++cb) {
-    const int c0 = 128 * half + 64 * cb;
-    float t[64];
-    tmem_ld_x32(tl + kM_ColAcc + c0, *reinterpret_cast<float(*)[32]>(&t[0]));
-    tmem_ld_x32(tl + kM_ColAcc + c0 + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
-    tmem_ld_wait();
-    const float4* b4 = reinterpret_cast<const float4*>(b + c0);
-    const float4* w4 = reinterpret_cast<const float4*>(w_alpha + c0);
-    uint32_t pk[32];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 bb = b4[j];
-      float v0 = t[4 * j] + bb.x, v1 = t[4 * j + 1] + bb.y, v2 = t[4 * j + 2] + bb.z, v3 = t[4 * j + 3] + bb.w;
-      if (kRelu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-      if (kAlpha) {
-        const float4 ww = w4[j];
-        acc4[0] = fmaf(v0, ww.x, acc4[0]); acc4[1] = fmaf(v1, ww.y, acc4[1]);
-        acc4[2] = fmaf(v2, ww.z, acc4[2]); acc4[3] = fmaf(v3, ww.w, acc4[3]);
-      }
-      pk[2 * j] = pack_bf16x2(v0, v1);
-      pk[2 * j + 1] = pack_bf16x2(v2, v3);
-    }
-    tmem_st_u32(tl + kM_ColH + c0 / 2, pk);
-  }
-  tmem_st_wait();
-  return (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
-// 80 packed columns of a bf16 token row (160 values), split between the two halves of the row
-__device__ __forceinline__ void token_to_tmem(const __nv_bfloat16* row, bool valid, int half, uint32_t taddr) {
-  uint32_t w[40];
-  const uint4* src = reinterpret_cast<const uint4*>(row) + 10 * half;     // 80 bf16 = 10 x 16 bytes per half
+// The MMA warp's program for one tile, as data (keeps its code one small loop that stays in the
+// instruction cache).  A step = 8 MMAs = one half (K = 128) of a ring slot; a slot = the weights
+// of one half-layer (128 rows x K = 256, 64 KB), numbered 0..21 within a tile:
+//   0,1 L0 h0/h1 | 2L+2, 2L+3 for L1..L4 | 10 L5.h0 x part, 11 L5.h0 h part, 12 L5.h1 x, 13 L5.h1 h |
+//   14..19 L6, L7, feature | 20 views tok1 part, 21 views feature part.
+// Issue-side budget (tools/ubench_tc.cu, in-kernel traces): the tensor pipe queues only ~3 MMAs
+// (~190 cycles) and every mbarrier probe costs the issuing warp ~100 cycles, not pipelined.  So the
+// MMA warp waits on at most one barrier per step: the "weights landed" barriers are waited on by the
+// EPILOGUE warps (which have slack) before they arrive on a_bar -- a_bar0/1 then stand for
+// "operand ready, accumulator drained, weights of the steps up to the next a_bar wait landed".
+// wait bits: 1 a_bar0, 2 a_bar1, 4 full barrier of the own slot (the second and later slots of L5 and
+// views, which cannot be resident early enough in a 3-slot ring); commit: 1 d_bar0, 2 k_bar, 3 d_bar1; sub = slot half;
+// K is padded to whole slots: x (K = 224) and tok1 (K = 160) read on into TMEM columns that hold
+// finite values (stale PE, zeroed [496,512)) against zero weight columns.
+// One packed word per step (a single constant load, prefetched one step ahead): bits 0-1 (acol - 256) / 64,
+// 2-4 wait, 5 dhalf, 6 fresh, 7-8 commit (after the step), 9-10 mode (0 = first half of the slot, 8 MMAs;
+// 1 = second half, 8 MMAs, releases the slot; 2 = whole slot, 16 MMAs, releases it), 11 midk (commit k_bar
+// after the first 8 MMAs of a whole-slot step).  Steps are as long as the dependencies allow: every step
+// boundary costs the MMA warp ~250 cycles of descriptor set-up and bookkeeping that the shallow tensor
+// queue (~3 MMAs) cannot hide.
+#define MPS_OP(acol, wait, dhalf, fresh, commit, mode, midk) \
+  ((uint32_t)(((acol) - 256) / 64) | ((wait) << 2) | ((dhalf) << 5) | ((fresh) << 6) | ((commit) << 7) | ((mode) << 9) | ((midk) << 11))
+#define MPS_M_HIDDEN MPS_OP(256, 1, 0, 1, 0, 0, 0), MPS_OP(320, 2, 0, 0, 1, 1, 0), MPS_OP(256, 0, 1, 1, 3, 2, 1)
+__constant__ uint32_t kMSchedule[] = {
+    MPS_OP(384, 1 | 2, 0, 1, 1, 2, 0), MPS_OP(384, 0, 1, 1, 3, 2, 1),                                        // L0: A = x
+    MPS_M_HIDDEN, MPS_M_HIDDEN, MPS_M_HIDDEN, MPS_M_HIDDEN,                                                  // L1..L4
+    MPS_OP(384, 1, 0, 1, 0, 2, 0), MPS_OP(256, 4, 0, 0, 0, 0, 0), MPS_OP(320, 2, 0, 0, 1, 1, 0),             // L5: [x | h], x part first
+    MPS_OP(384, 4, 1, 1, 0, 2, 0), MPS_OP(256, 4, 1, 0, 3, 2, 1),
+    MPS_M_HIDDEN, MPS_M_HIDDEN, MPS_M_HIDDEN,                                                                // L6, L7, feature
+    MPS_OP(384, 1, 0, 1, 0, 2, 0), MPS_OP(256, 4, 0, 0, 0, 0, 0), MPS_OP(320, 2, 0, 0, 1, 1, 0),             // views: [tok1 | feature]
+    MPS_OP(384, 1 | 2, 0, 1, 1, 2, 0)};                                                                      // (prefetch target past the end = step 0)
+#undef MPS_M_HIDDEN
+struct MOp {
+  uint32_t w;
+  __device__ __forceinline__ uint32_t acol() const { return 256u + 64u * (w & 3u); }
+  __device__ __forceinline__ uint32_t wait() const { return (w >> 2) & 7u; }
+  __device__ __forceinline__ uint32_t dcol() const { return ((w >> 5) & 1u) * 128u; }
+  __device__ __forceinline__ bool fresh() const { return (w >> 6) & 1u; }
+  __device__ __forceinline__ uint32_t commit() const { return (w >> 7) & 3u; }
+  __device__ __forceinline__ uint32_t mode() const { return (w >> 9) & 3u; }
+  __device__ __forceinline__ bool midk() const { return (w >> 11) & 1u; }
+};
+constexpr int kMScheduleLen = 2 + 7 * 3 + 5 + 3;
+// slots whose arrival the epilogue of (layer L, half j) vouches for when it arrives on a_bar[j]: {first, count}
+__constant__ uint8_t kMCarry[9][2][2] = {
+    {{2, 1}, {3, 1}}, {{4, 1}, {5, 1}}, {{6, 1}, {7, 1}}, {{8, 1}, {9, 1}}, {{10, 1}, {0, 0}},
+    {{14, 1}, {15, 1}}, {{16, 1}, {17, 1}}, {{18, 1}, {19, 1}}, {{20, 1}, {0, 0}}};
+static_assert(sizeof(kMSchedule) / sizeof(uint32_t) == kMScheduleLen + 1, "M schedule length");
+
+// 640 threads = 5 warpgroups: four epilogue warpgroups (16 warps, four threads per row: thread
+// (r = tid & 127, q = tid >> 7) owns 32 of the 128 columns of an accumulator half; raised to 104
+// registers) and one holding the producer warp, the MMA warp and two idle warps (lowered to 40).
+constexpr int kMThreads = 640, kMEpiThreads = 512, kMProdWarp = 16, kMMmaWarp = 17;
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+__device__ __forceinline__ void m_epi_bar() { named_bar_sync(1, kMEpiThreads); }
+
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+
+// 16 elements (8 packed words) [16 q, 16 q + 16) of the 39-wide positional code [x, sin(f0 x), cos(f0 x), ...],
+// f_k = pi 2^k (run_nerf_helpers.py:337-353); elements >= 39 are zero padding.  One sincospi per
+// channel, then the double-angle recurrence for the 5 higher octaves (abs error < 3e-6 after 5
+// doublings, three orders of magnitude below the bf16 rounding of the operand).
+__device__ __forceinline__ void pe_words(const float (&xc)[3], int q, uint32_t (&pk)[8]) {
+  float pe[64];
 #pragma unroll
-  for (int u = 0; u < 10; ++u) {
-    const uint4 t = valid ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+  for (int e = 0; e < 64; ++e) pe[e] = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    pe[ch] = xc[ch];
+    float s, c;
+    sincospif(xc[ch], &s, &c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      pe[3 + 6 * k + ch] = s;
+      pe[3 + 6 * k + 3 + ch] = c;
+      const float s2 = 2.0f * s * c, c2 = fmaf(-2.0f * s, s, 1.0f);
+      s = s2; c = c2;
+    }
+  }
+#pragma unroll
+  for (int w2 = 0; w2 < 8; ++w2) {      // q is warp-uniform: three selects per word instead of four code copies
+    const float lo = q == 0 ? pe[2 * w2] : q == 1 ? pe[16 + 2 * w2] : q == 2 ? pe[32 + 2 * w2] : pe[48 + 2 * w2];
+    const float hi = q == 0 ? pe[2 * w2 + 1] : q == 1 ? pe[16 + 2 * w2 + 1] : q == 2 ? pe[32 + 2 * w2 + 1] : pe[48 + 2 * w2 + 1];
+    pk[w2] = pack_bf16x2(lo, hi);
+  }
+}
+
+// this thread's 20 packed columns of a bf16 token row (160 values split between the four quarters).
+// Unconditional loads (the caller clamps the row index): nothing consumes the registers until the
+// token is stored, so the global latency hides behind the work in between.
+__device__ __forceinline__ void token_load(const __nv_bfloat16* row, int q, uint32_t (&w)[20]) {
+  const uint4* src = reinterpret_cast<const uint4*>(row) + 5 * q;     // 40 bf16 = 5 x 16 bytes per quarter
+#pragma unroll
+  for (int u = 0; u < 5; ++u) {
+    const uint4 t = __ldg(src + u);
     w[4 * u] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
   }
-#pragma unroll
-  for (int i = 0; i < 5; ++i) tmem_st_x8(taddr + 40 * half + 8 * i, *reinterpret_cast<const uint32_t(*)[8]>(&w[8 * i]));
 }
-
-// 32 elements (16 packed words) of the 39-wide positional code [x, sin(f0 x), cos(f0 x), ...]
-// (run_nerf_helpers.py:337-353; cos as sin(. + fl(pi/2))); elements >= 39 are zero padding.
-template <int kHalf>
-__device__ __forceinline__ void pe_words(const float (&xc)[3], uint32_t (&pk)[16]) {
+__device__ __forceinline__ void token_store(uint32_t taddr, int q, const uint32_t (&w)[20]) {
 #pragma unroll
-  for (int w2 = 0; w2 < 16; ++w2) {
-    float v[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      constexpr int kBase = 32 * kHalf;
-      const int e = kBase + 2 * w2 + q;            // compile-time after unrolling
-      float val = 0.f;
-      if (e < 3) val = xc[e];
-      else if (e < 39) {
-        const int k = (e - 3) / 6, ch = (e - 3) % 3;
-        const bool is_cos = ((e - 3) % 6) >= 3;
-        val = sinf(fmaf(xc[ch], 3.14159265358979323846f * (float)(1 << k), is_cos ? 1.57079632679489661923f : 0.0f));
-      }
-      v[q] = val;
-    }
-    pk[w2] = pack_bf16x2(v[0], v[1]);
-  }
+  for (int i = 0; i < 5; ++i) tmem_st_x4(taddr + 20 * q + 4 * i, &w[4 * i]);
 }
 
 template <int kC>
-__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
+__global__ void __launch_bounds__(kMThreads, 1) mlp_tc_kernel(const MArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Pipe* pipe = reinterpret_cast<Pipe*>(smem + kM_PIPE);
   float* FP = reinterpret_cast<float*>(smem + kM_FP);
@@ -639,17 +751,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
   const int64_t ntiles = (a.count + 127) / 128;
   const uint32_t crank = (kC > 1) ? cluster_ctarank() : 0u;
   const int64_t ncl = gridDim.x / kC, cid = blockIdx.x / kC;
+  const int64_t tstride = ncl * kC;
 
   if (tid == 0) {
     for (int i = 0; i < kM_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], kC); }
-    mbar_init(&pipe->a_bar, kEpiThreads);
-    mbar_init(&pipe->d_bar, 1);
+    mbar_init(&pipe->a_bar[0], kMEpiThreads);
+    mbar_init(&pipe->a_bar[1], kMEpiThreads);
+    mbar_init(&pipe->d_bar[0], 1);
+    mbar_init(&pipe->d_bar[1], 1);
+    mbar_init(&pipe->k_bar, 1);
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
+  if (warp == kMMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
   {
     const float* src = reinterpret_cast<const float*>(a.blob + kFloatOff) + kTFloats;
-    for (int i = tid; i < kMFloats; i += kTcThreads) FP[i] = src[i];
+    for (int i = tid; i < kMFloats; i += kMThreads) FP[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -657,59 +773,86 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
   tc_fence_after();
   const uint32_t tm = pipe->tmem_base;
 
-  if (warp == kProdWarp) {
-    if (lane == 0) {
-      Producer<kM_Slots, kM_SlotBytes, kC> P{pipe, smem + kM_RING, crank};
-      P.pf = Prof{a.prof != 0, 0};
-      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
-        const uint8_t* src = a.blob + kTBytes;
-        for (int i = 0; i < 40; ++i) P.push(src, 32768);      // L0..L7, feature: 256-row chunks
-        for (int i = 0; i < 7; ++i) P.push(src, 16384);       // views: 128-row chunks
-      }
-      if (a.prof) atomicAdd(&g_prof[1][6], (unsigned long long)P.acc_e);
+  if (warp >= 16) {
+    reg_dec<40>();           // fifth warpgroup: producer, MMA issuer, two idle warps
+  if (warp == kMProdWarp) {
+    RingProducer<kM_Slots, kM_SlotBytes, kC> P{pipe, smem + kM_RING, crank};
+    P.pf = Prof{a.prof == 1 && lane == 0, 0};
+    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += tstride) {
+      const uint8_t* src = a.blob + kTBytes;
+      for (int i = 0; i < kM_SlotsPerTile; ++i) P.push(src, kM_SlotBytes);
     }
-  } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      Consumer<kM_Slots, kM_SlotBytes, kC> Cn{pipe, smem_u32(smem + kM_RING)};
-      Cn.pf = Prof{a.prof != 0, 0};
-      const long long t_begin = clock64();
-      // A (TMEM at column acol, `ksteps` valid K=16 steps out of `chunks` weight chunks) -> ACC
-      auto gemm = [&](uint32_t acol, int ksteps, int chunks, int N, bool accumulate) {
-        const uint32_t idesc = instr_desc_bf16(N);
-        for (int c = 0; c < chunks; ++c) {
-          const uint32_t b0 = Cn.slot_wait();
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const int ks = 4 * c + k4;
-            if (ks < ksteps)
-              mma_bf16_ts(tm + kM_ColAcc, tm + acol + ks * 8, smem_desc_sw128(b0 + k4 * 32), idesc, (accumulate || ks > 0) ? 1u : 0u);
-          }
-          Cn.slot_free();
+    if (P.pf.on) atomicAdd(&g_prof[1][6], (unsigned long long)P.acc_e);
+  } else if (warp == kMMmaWarp) {
+    // The whole warp runs the schedule; one elected lane issues the tcgen05 instructions.
+    const uint32_t ring_addr = smem_u32(smem + kM_RING);
+    constexpr uint32_t idesc = instr_desc_bf16(128);
+    uint32_t pa0 = 0, pa1 = 0, slot = 0, phase = 0, opw = kMSchedule[0];
+    Trace tr{false, 0, 0};
+    Prof pf{a.prof == 1 && lane == 0, 0};
+    long long acc_a = 0;
+    const long long t_begin = clock64();
+    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += tstride) {
+      tr.on = (a.prof == 2) && blockIdx.x == 0 && lane == 0 && tbase == cid * kC + tstride;
+      if (a.prof == 5 && blockIdx.x == 0 && lane == 0) { Trace t5{true, tr.n, 0}; t5.ev(30); tr.n = t5.n; }
+#pragma unroll 1
+      for (int o = 0; o < kMScheduleLen; ++o) {
+        const MOp op{opw};
+        opw = kMSchedule[o + 1];               // prefetch the next step's word (entry [len] = step 0)
+        const uint32_t wait = op.wait(), mode = op.mode();
+        // operands first (uniform-datapath work), then the barrier probes, then the MMAs back to back
+        const uint64_t bdesc = smem_desc_sw128(ring_addr + slot * kM_SlotBytes + (mode == 1 ? 32768u : 0u));
+        const uint32_t d_addr = tm + op.dcol(), a_addr = tm + op.acol(), commit = op.commit();
+        const uint32_t acc0 = op.fresh() ? 0u : 1u;
+        if (wait) {
+          tr.ev(20);
+          pf.start();
+          if (wait & 1) { mbar_wait(&pipe->a_bar[0], pa0 & 1); ++pa0; }
+          if (wait & 2) { mbar_wait(&pipe->a_bar[1], pa1 & 1); ++pa1; }
+          if (wait & 4) mbar_wait(&pipe->full[slot], phase);
+          pf.stop(acc_a);
+          tc_fence_after();
+          tr.ev(21);
         }
-      };
-      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
-        Cn.wait_a(); gemm(kM_ColX, 14, 4, 256, false); Cn.done();                                   // L0
-        for (int L = 1; L < 5; ++L) { Cn.wait_a(); gemm(kM_ColH, 16, 4, 256, false); Cn.done(); }   // L1..L4
-        Cn.wait_a(); gemm(kM_ColX, 14, 4, 256, false); gemm(kM_ColH, 16, 4, 256, true); Cn.done();  // L5: [x | h]
-        for (int L = 6; L < 8; ++L) { Cn.wait_a(); gemm(kM_ColH, 16, 4, 256, false); Cn.done(); }   // L6, L7
-        Cn.wait_a(); gemm(kM_ColH, 16, 4, 256, false); Cn.done();                                   // feature
-        Cn.wait_a(); gemm(kM_ColX, 10, 3, 128, false); gemm(kM_ColH, 16, 4, 128, true); Cn.done();  // views: [tok1 | feature]
-      }
-      if (a.prof) {
-        atomicAdd(&g_prof[1][3], (unsigned long long)Cn.acc_a);
-        atomicAdd(&g_prof[1][4], (unsigned long long)Cn.acc_w);
-        atomicAdd(&g_prof[1][5], (unsigned long long)(clock64() - t_begin));
+        if (elect_one()) {       // K-steps of A (TMEM columns acol ..) x 128 weight rows -> accumulator half
+          // descriptor of K-step k = base + (chunk k / 4) * 16 KB + (k % 4) * 32 B, in 16-byte units
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mma_bf16_ts(d_addr, a_addr + k * 8, bdesc + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), idesc, k ? 1u : acc0);
+          if (mode == 2) {
+            if (op.midk()) mma_commit(&pipe->k_bar);
+#pragma unroll
+            for (int k = 8; k < 16; ++k)
+              mma_bf16_ts(d_addr, a_addr + k * 8, bdesc + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), idesc, 1u);
+          }
+          if (mode != 0) {          // slot consumed
+            if (kC == 1) mma_commit(&pipe->empty[slot]);
+            else mma_commit_mc(&pipe->empty[slot], (uint16_t)((1u << kC) - 1u));
+          }
+          if (commit) mma_commit(commit == 1 ? &pipe->d_bar[0] : &pipe->d_bar[1]);
+        }
+        __syncwarp();
+        if (commit) tr.ev(4 + commit);
+        if (mode != 0) { if (++slot == kM_Slots) { slot = 0; phase ^= 1; } }
       }
     }
+    if (pf.on) {
+      atomicAdd(&g_prof[1][3], (unsigned long long)acc_a);
+      atomicAdd(&g_prof[1][5], (unsigned long long)(clock64() - t_begin));
+    }
+  }
   } else {
-    const int r = tid & 127, half = tid >> 7;
+    reg_inc<104>();
+    const int r = tid & 127, q = tid >> 7;
     const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t g = 0;
-    Prof pf{a.prof != 0 && tid == 0, 0};
+    uint32_t pd[2] = {0, 0}, pk_ = 0;
+    Prof pf{a.prof == 1 && tid == 0, 0};
     long long acc_d = 0, acc_tl = 0, n_tiles = 0;
     const long long t_begin = clock64();
-    auto hand_over = [&]() { tc_fence_before(); mbar_arrive(&pipe->a_bar); };
-    auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar, g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
+    Trace tr{false, 0, 256};
+    auto wait_d = [&](int j) { tr.ev(10 + j); pf.start(); mbar_wait(&pipe->d_bar[j], pd[j] & 1); pf.stop(acc_d); ++pd[j]; tc_fence_after(); tr.ev(12 + j); };
+    auto wait_k = [&]() { pf.start(); mbar_wait(&pipe->k_bar, pk_ & 1); pf.stop(acc_d); ++pk_; tc_fence_after(); };
+    auto arrive = [&](int j) { tc_fence_before(); mbar_arrive(&pipe->a_bar[j]); tr.ev(16 + j); };
     const float* bias = FP;                       // 8 x 256
     const float* w_alpha = FP + 2048;
     const float* b_feat = FP + 2304;
@@ -717,67 +860,160 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
     const float* w_rgb = FP + 2688;               // 3 x 128
     const float* b_tail = FP + 3072;              // b_alpha, b_rgb[3]
 
-    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
+    // one warp per a_bar waits for the weight slots [first, first + n) (tile-relative numbering) to land
+    int64_t seq0 = 0;            // ring sequence number of this tile's slot 0
+    auto vouch = [&](int j, int first_slot, int n) {
+      if (warp == 4 * j) {
+        for (int u = 0; u < n; ++u) {
+          const int64_t sq = seq0 + first_slot + u;
+          mbar_wait(&pipe->full[sq % kM_Slots], (uint32_t)((sq / kM_Slots) & 1));
+        }
+      }
+    };
+    // The next tile's x is fetched in steps spread over the current tile: global loads before the
+    // feature layer, positional code after it, TMEM store inside the views epilogue.  Rows past the
+    // end are clamped to the last point: rows are independent and their results are never written.
+    uint32_t xw[20], xpe[8];
+    float xcn[3];
+    auto load_x = [&](int64_t tile) {
+      const int64_t i = min(tile * 128 + r, a.count - 1);
+      token_load(a.tok0 + i * kTokLd, q, xw);
+      xcn[0] = __ldg(a.xc + 3 * i); xcn[1] = __ldg(a.xc + 3 * i + 1); xcn[2] = __ldg(a.xc + 3 * i + 2);
+    };
+    auto store_x = [&](int64_t seq_next) {       // XT = [tok0 | 0 | PE6(xc) | 0]; this thread: 20 token columns + 8 PE columns
+      token_store(tl + kM_ColX, q, xw);
+      tmem_st_x8(tl + kM_ColX + 80 + 8 * q, xpe);
+      if (warp == 0) mbar_wait(&pipe->full[seq_next % kM_Slots], (uint32_t)((seq_next / kM_Slots) & 1));
+      if (warp == 4) mbar_wait(&pipe->full[(seq_next + 1) % kM_Slots], (uint32_t)(((seq_next + 1) / kM_Slots) & 1));
+      tmem_st_wait();
+      arrive(0); arrive(1);
+    };
+    // half j of a hidden layer: 32 accumulator columns of this thread -> (+bias, ReLU) -> bf16 x2 -> HT
+    auto epi_half = [&](auto relu_c, auto alpha_c, int L, int j, const float* __restrict__ b, float& alpha) {
+      constexpr bool relu = decltype(relu_c)::value, with_alpha = decltype(alpha_c)::value;
+      const int c0 = 128 * j + 32 * q;
+      wait_d(j);
+      float t[32];
+      tmem_ld_x32(tl + kM_ColAcc + c0, t);
+      vouch(j, kMCarry[L][j][0], kMCarry[L][j][1]);      // overlaps the TMEM load
+      tmem_ld_wait();
+      tr.ev(18);
+      const float4* b4 = reinterpret_cast<const float4*>(b + c0);
+      const float4* w4 = reinterpret_cast<const float4*>(w_alpha + c0);
+      uint32_t pk[16];
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 bb = b4[u];
+        const float v0 = t[4 * u] + bb.x, v1 = t[4 * u + 1] + bb.y, v2 = t[4 * u + 2] + bb.z, v3 = t[4 * u + 3] + bb.w;
+        if (with_alpha) {
+          const float4 ww = w4[u];
+          a4[0] = fmaf(fmaxf(v0, 0.f), ww.x, a4[0]); a4[1] = fmaf(fmaxf(v1, 0.f), ww.y, a4[1]);
+          a4[2] = fmaf(fmaxf(v2, 0.f), ww.z, a4[2]); a4[3] = fmaf(fmaxf(v3, 0.f), ww.w, a4[3]);
+        }
+        if (relu) { pk[2 * u] = pack_relu_bf16x2(v0, v1); pk[2 * u + 1] = pack_relu_bf16x2(v2, v3); }
+        else { pk[2 * u] = pack_bf16x2(v0, v1); pk[2 * u + 1] = pack_bf16x2(v2, v3); }
+      }
+      if (with_alpha) alpha += (a4[0] + a4[1]) + (a4[2] + a4[3]);
+      if (j == 0) wait_k();                      // [h1: K0] has read the old K-half 0
+      tmem_st_u16(tl + kM_ColH + c0 / 2, pk);
+    };
+    using T_ = std::true_type; using F_ = std::false_type;
+
+    if (q == 0) {      // K padding of the x / tok1 operand: TMEM columns [496, 512) must hold finite values
+      const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      tmem_st_u16(tl + 496, z);
+      tmem_st_wait();
+    }
+    bool first = true;
+    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += tstride) {
       const int64_t tile = tbase + crank;
       const int64_t i = tile * 128 + r;
       const bool valid = i < a.count;
-      {
-        // ---- tile load: XT = [tok0 | 0 | PE6(xc) | 0]; this thread: 40 token columns + 16 PE columns
+      const bool has_next = tbase + tstride < ntiles;
+      tr.on = (a.prof == 2) && blockIdx.x == 0 && tid == 0 && tbase == cid * kC + tstride;
+      if (first) {
         pf.start();
-        token_to_tmem(a.tok0 + (valid ? i : 0) * kTokLd, valid, half, tl + kM_ColX);
-        float xc[3] = {0.f, 0.f, 0.f};
-        if (valid) { xc[0] = a.xc[3 * i]; xc[1] = a.xc[3 * i + 1]; xc[2] = a.xc[3 * i + 2]; }
-        uint32_t pk[16];
-        if (half == 0) pe_words<0>(xc, pk); else pe_words<1>(xc, pk);
-        tmem_st_u16(tl + kM_ColX + 80 + 16 * half, pk);
-        tmem_st_wait();
+        load_x(tile);
+        pe_words(xcn, q, xpe);
+        store_x(0);
         pf.stop(acc_tl);
-        hand_over();
+        first = false;
       }
       float alpha = 0.f;
-      for (int L = 0; L < 9; ++L) {          // L0..L7 (ReLU) and 8 = feature (no activation)
-        wait_d();
-        if (L == 5)                          // x is dead after layer 5: XT <- tok1 for the views layer
-          token_to_tmem(a.tok1 + (valid ? i : 0) * kTokLd, valid, half, tl + kM_ColX);
-        // the layer kind is warp-uniform: pick a fully specialised epilogue (no per-element branches)
-        if (L == 7) alpha = epi_hidden<true, true>(tl, half, bias + 256 * 7, w_alpha);   // + alpha_linear on fp32 acts
-        else if (L == 8) epi_hidden<false, false>(tl, half, b_feat, nullptr);
-        else epi_hidden<true, false>(tl, half, bias + 256 * L, nullptr);
-        hand_over();
+#pragma unroll 1
+      for (int L = 0; L < 5; ++L) {          // L0..L4
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          epi_half(T_{}, F_{}, L, j, bias + 256 * L, alpha);
+          tmem_st_wait();
+          arrive(j);
+        }
+      }
+      {                                      // L5: afterwards x is dead and XT takes tok1 for the views layer
+        uint32_t t1[20];
+        token_load(a.tok1 + min(i, a.count - 1) * kTokLd, q, t1);
+        epi_half(T_{}, F_{}, 5, 0, bias + 256 * 5, alpha);
+        tmem_st_wait();
+        arrive(0);
+        epi_half(T_{}, F_{}, 5, 1, bias + 256 * 5, alpha);
+        token_store(tl + kM_ColX, q, t1);    // layer 5 has been accumulated (d_bar1): nobody reads x any more
+        tmem_st_wait();
+        arrive(1);
+      }
+#pragma unroll 1
+      for (int L = 6; L < 8; ++L) {          // L6, L7 (+ alpha_linear on the fp32 activations of L7)
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          if (L == 7) epi_half(T_{}, T_{}, L, j, bias + 256 * L, alpha); else epi_half(T_{}, F_{}, L, j, bias + 256 * L, alpha);
+          tmem_st_wait();
+          arrive(j);
+        }
+      }
+      if (has_next) load_x(tile + tstride);  // in flight during the feature layer
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {          // feature (no activation)
+        epi_half(F_{}, F_{}, 8, j, b_feat, alpha);
+        tmem_st_wait();
+        arrive(j);
       }
       {
         // ---- views layer epilogue: relu -> rgb_linear on CUDA cores -> raw[pid] = (rgb, alpha)
-        wait_d();
-        float c0[2] = {0.f, 0.f}, c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
-        float t[64];
-        tmem_ld_x32(tl + kM_ColAcc + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
-        tmem_ld_x32(tl + kM_ColAcc + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
+        if (has_next) pe_words(xcn, q, xpe);
+        wait_d(0);
+        float t[32];
+        tmem_ld_x32(tl + kM_ColAcc + 32 * q, t);
         tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(b_views + 64 * half);
-        const float4* r0 = reinterpret_cast<const float4*>(w_rgb + 64 * half);
-        const float4* r1 = reinterpret_cast<const float4*>(w_rgb + 128 + 64 * half);
-        const float4* r2 = reinterpret_cast<const float4*>(w_rgb + 256 + 64 * half);
+        if (has_next) store_x(seq0 + kM_SlotsPerTile);   // ACC0 and XT are free: the next tile's layer 0 starts now
+        float c0[2] = {0.f, 0.f}, c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
+        const float4* b4 = reinterpret_cast<const float4*>(b_views + 32 * q);
+        const float4* r0 = reinterpret_cast<const float4*>(w_rgb + 32 * q);
+        const float4* r1 = reinterpret_cast<const float4*>(w_rgb + 128 + 32 * q);
+        const float4* r2 = reinterpret_cast<const float4*>(w_rgb + 256 + 32 * q);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 bb = b4[j], w0 = r0[j], w1 = r1[j], w2 = r2[j];
-          const float v0 = fmaxf(t[4 * j] + bb.x, 0.f), v1 = fmaxf(t[4 * j + 1] + bb.y, 0.f);
-          const float v2 = fmaxf(t[4 * j + 2] + bb.z, 0.f), v3 = fmaxf(t[4 * j + 3] + bb.w, 0.f);
+        for (int u = 0; u < 8; ++u) {
+          const float4 bb = b4[u], w0 = r0[u], w1 = r1[u], w2 = r2[u];
+          const float v0 = fmaxf(t[4 * u] + bb.x, 0.f), v1 = fmaxf(t[4 * u + 1] + bb.y, 0.f);
+          const float v2 = fmaxf(t[4 * u + 2] + bb.z, 0.f), v3 = fmaxf(t[4 * u + 3] + bb.w, 0.f);
           c0[0] = fmaf(v0, w0.x, c0[0]); c0[1] = fmaf(v1, w0.y, c0[1]); c0[0] = fmaf(v2, w0.z, c0[0]); c0[1] = fmaf(v3, w0.w, c0[1]);
           c1[0] = fmaf(v0, w1.x, c1[0]); c1[1] = fmaf(v1, w1.y, c1[1]); c1[0] = fmaf(v2, w1.z, c1[0]); c1[1] = fmaf(v3, w1.w, c1[1]);
           c2[0] = fmaf(v0, w2.x, c2[0]); c2[1] = fmaf(v1, w2.y, c2[1]); c2[0] = fmaf(v2, w2.z, c2[0]); c2[1] = fmaf(v3, w2.w, c2[1]);
         }
-        if (half == 1)
-          *reinterpret_cast<float4*>(PART + 4 * r) = make_float4(c0[0] + c0[1], c1[0] + c1[1], c2[0] + c2[1], alpha);
-        epi_bar();
-        if (half == 0 && valid) {
-          const float4 o = *reinterpret_cast<const float4*>(PART + 4 * r);
+        if (q != 0)
+          *reinterpret_cast<float4*>(PART + 4 * (128 * (q - 1) + r)) = make_float4(c0[0] + c0[1], c1[0] + c1[1], c2[0] + c2[1], alpha);
+        m_epi_bar();
+        if (q == 0 && valid) {
+          const float4 o1 = *reinterpret_cast<const float4*>(PART + 4 * r);
+          const float4 o2 = *reinterpret_cast<const float4*>(PART + 4 * (128 + r));
+          const float4 o3 = *reinterpret_cast<const float4*>(PART + 4 * (256 + r));
           reinterpret_cast<float4*>(a.raw)[a.act_pid[i]] =
-              make_float4(c0[0] + c0[1] + o.x + b_tail[1], c1[0] + c1[1] + o.y + b_tail[2],
-                          c2[0] + c2[1] + o.z + b_tail[3], alpha + o.w + b_tail[0]);
+              make_float4(c0[0] + c0[1] + (o1.x + o2.x + o3.x) + b_tail[1], c1[0] + c1[1] + (o1.y + o2.y + o3.y) + b_tail[2],
+                          c2[0] + c2[1] + (o1.z + o2.z + o3.z) + b_tail[3], alpha + (o1.w + o2.w + o3.w) + b_tail[0]);
         }
-        epi_bar();      // PART is rewritten by the next tile
+        m_epi_bar();      // PART is rewritten by the next tile
       }
       ++n_tiles;
+      seq0 += kM_SlotsPerTile;
     }
     if (pf.on) {
       atomicAdd(&g_prof[1][0], (unsigned long long)acc_d);
@@ -789,7 +1025,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const MArgs a) {
   tc_fence_before();
   __syncthreads();
   if (kC > 1) cluster_sync_all();
-  if (warp == kMmaWarp) tmem_dealloc(tm, 512);
+  if (warp == kMMmaWarp) tmem_dealloc(tm, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -970,12 +1206,12 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
   }
   static int prof = -1;
-  if (prof < 0) { const char* e = getenv("MPSNERF_TC_PROF"); prof = (e && atoi(e)) ? 1 : 0; }
+  if (prof < 0) { const char* e = getenv("MPSNERF_TC_PROF"); prof = e ? atoi(e) : 0; }
   TArgs ta{tokens, ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof};
   MArgs ma{tok0, tok1, xc, count, static_cast<const uint8_t*>(packed), act_pid + first, raw, prof};
   const int ppt = 128 / n_views;
   const int64_t t_tiles = (count + ppt - 1) / ppt, m_tiles = (count + 127) / 128;
-  auto launch = [&](auto kernel, const auto& args, size_t smem_bytes, int64_t tiles, int kc) -> cudaError_t {
+  auto launch = [&](auto kernel, const auto& args, size_t smem_bytes, int64_t tiles, int kc, int threads) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int64_t ctas = (tiles + kc - 1) / kc * kc;                  // whole clusters
@@ -983,7 +1219,7 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
     if (ctas > cap) ctas = cap;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3(kTcThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -995,14 +1231,21 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args);
   };
-#define MPS_T_CASE(V_, C_) if (n_views == V_ && cluster == C_) MPS_CUDA(launch(xformer_tc_kernel<V_, C_>, ta, kT_Smem, t_tiles, C_));
+#define MPS_T_CASE(V_, C_) if (n_views == V_ && cluster == C_) MPS_CUDA(launch(xformer_tc_kernel<V_, C_>, ta, kT_Smem, t_tiles, C_, kTcThreads));
   MPS_T_CASE(2, 1) MPS_T_CASE(2, 2) MPS_T_CASE(2, 4)
   MPS_T_CASE(3, 1) MPS_T_CASE(3, 2) MPS_T_CASE(3, 4)
   MPS_T_CASE(4, 1) MPS_T_CASE(4, 2) MPS_T_CASE(4, 4)
 #undef MPS_T_CASE
-  if (cluster == 1) MPS_CUDA(launch(mlp_tc_kernel<1>, ma, kM_Smem, m_tiles, 1));
-  if (cluster == 2) MPS_CUDA(launch(mlp_tc_kernel<2>, ma, kM_Smem, m_tiles, 2));
-  if (cluster == 4) MPS_CUDA(launch(mlp_tc_kernel<4>, ma, kM_Smem, m_tiles, 4));
+  if (cluster == 1) MPS_CUDA(launch(mlp_tc_kernel<1>, ma, kM_Smem, m_tiles, 1, kMThreads));
+  if (cluster == 2) MPS_CUDA(launch(mlp_tc_kernel<2>, ma, kM_Smem, m_tiles, 2, kMThreads));
+  if (cluster == 4) MPS_CUDA(launch(mlp_tc_kernel<4>, ma, kM_Smem, m_tiles, 4, kMThreads));
+  return MPSNERF_OK;
+}
+
+// Debug: copy the event trace (512 entries, see g_trace).
+extern "C" int mpsnerf_debug_read_trace(unsigned long long* host_out) {
+  MPS_REQUIRE(host_out != nullptr);
+  MPS_CUDA(cudaMemcpyFromSymbol(host_out, mps::g_trace, sizeof(unsigned long long) * 512));
   return MPSNERF_OK;
 }
 

@@ -43,9 +43,50 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (issued early, consumed late: hides the barrier round trip behind other work)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Probe four barriers with ONE round trip (the four test_wait are issued back to back, their results
+// are consumed afterwards); returns a bit mask of the completed ones.  A barrier round trip costs
+// 100-250 cycles inside the fused kernels, so dependent waits are batched, never chained.
+__device__ __forceinline__ uint32_t mbar_test4(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2, uint32_t p2,
+                                               uint32_t b3, uint32_t p3) {
+  uint32_t m;
+  asm volatile(
+      "{\n\t.reg .pred q0, q1, q2, q3;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+      "selp.u32 t0, 1, 0, q0;\n\tselp.u32 t1, 2, 0, q1;\n\tselp.u32 t2, 4, 0, q2;\n\tselp.u32 t3, 8, 0, q3;\n\t"
+      "or.b32 t0, t0, t1;\n\tor.b32 t2, t2, t3;\n\tor.b32 %0, t0, t2;\n\t}"
+      : "=r"(m)
+      : "r"(b0), "r"(p0), "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3)
+      : "memory");
+  return m;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+
+// One lane of a fully converged warp (the same lane every time for a full mask).  tcgen05.mma /
+// commit / bulk copies are issued from `if (elect_one()) {...}` inside warp-uniform control flow:
+// their operands then live in uniform registers instead of going through per-use R2UR round trips
+// (a single-lane `if (lane == 0)` branch makes every UTCHMMA a slow waterfall loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------- bulk async copy global -> shared (1-D TMA)

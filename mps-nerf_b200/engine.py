@@ -71,7 +71,7 @@ class RenderEngine:
         assert precision in ("fp32", "bf16")
         self.net = net
         self.precision = precision
-        self.slab = slab or (32768 if precision == "fp32" else 262144)
+        self.slab = slab or (32768 if precision == "fp32" else 1 << 20)
         self.lib = _lib.load()
         self._ws = {}
         self._packed = None

@@ -7,10 +7,11 @@ Layout (bytes; every weight tile is K-major bf16 in SWIZZLE_128B chunks, see
       qkv_0[3 chunks x 192 rows]; then for h = 0..2: qkv_{h+1}[3 x 192], Wo_h[1 x 160];
       Wo_3[1 x 160]; W1[3 x 128]; W2[2 x 160]
       qkv_h rows = (q_h | k_h | v_h) = to_qkv rows 64h.., 256+64h.., 512+64h..   (K = 155 -> 192)
-  MLP (1 425 408 B):
-      L0[4 x 256] (K order: tok0 155, 5 zero, PE 39, zero to 256); L1..L4[4 x 256] each;
-      L5[x part 4 x 256 | h part 4 x 256]; L6, L7[4 x 256]; feature[4 x 256];
-      views[tok1 part 3 x 128 | feature part 4 x 128]
+  MLP (1 441 792 B = 44 ring slots of 2 chunks of 128 rows x 128 B), every 256-output layer split
+      into its two N-halves (output rows 0..127, then 128..255), each half 4 chunks (K = 256) per K part:
+      L0[h0 | h1] (K order: tok0 155, 5 zero, PE 39, zero to 256); L1..L4[h0 | h1] each;
+      L5[h0: x part, h part | h1: x part, h part]; L6, L7, feature[h0 | h1];
+      views[tok1 part 4 chunks | feature part 4 chunks] (128 outputs)
   fp32 section:
       per transformer layer 1088 floats: ln1_g, ln1_b, pend_in, ln2_g, ln2_b, pend_mid (160 each), b1 (128)
       then pend_out (160): the biases of to_out / net.3 are *deferred*: the residual stream in
@@ -24,7 +25,7 @@ from .engine import pack_kmajor_sw128
 
 T_LAYER_BYTES = 12 * 24576 + 4 * 20480 + 3 * 16384 + 2 * 20480
 T_BYTES = 2 * T_LAYER_BYTES
-M_BYTES = 40 * 32768 + 7 * 16384
+M_BYTES = 44 * 32768
 T_FLOATS = 2 * 1088 + 160
 M_FLOATS = 8 * 256 + 256 + 256 + 128 + 384 + 4
 FLOAT_OFFSET = T_BYTES + M_BYTES
@@ -75,16 +76,21 @@ def pack_weights_bf16(net, device=None):
         return o
 
     W = [sd[f"pts_linears.{i}.weight"] for i in range(8)]
-    parts.append(pack_kmajor_sw128(perm_x(W[0]), 256, 256))
+
+    def halves(*ws):      # per N-half (128 output rows): the K parts in issue order, 4 chunks of 64 each
+        for h in range(2):
+            for w in ws:
+                parts.append(pack_kmajor_sw128(w[128 * h:128 * h + 128], 128, 256))
+
+    halves(perm_x(W[0]))
     for i in range(1, 5):
-        parts.append(pack_kmajor_sw128(W[i], 256, 256))
-    parts.append(pack_kmajor_sw128(perm_x(W[5][:, :194]), 256, 256))
-    parts.append(pack_kmajor_sw128(W[5][:, 194:], 256, 256))
-    parts.append(pack_kmajor_sw128(W[6], 256, 256))
-    parts.append(pack_kmajor_sw128(W[7], 256, 256))
-    parts.append(pack_kmajor_sw128(sd["feature_linear.weight"], 256, 256))
+        halves(W[i])
+    halves(perm_x(W[5][:, :194]), W[5][:, 194:])
+    halves(W[6])
+    halves(W[7])
+    halves(sd["feature_linear.weight"])
     wv = sd["views_linear.weight"]
-    parts.append(pack_kmajor_sw128(wv[:, 256:411], 128, 192))
+    parts.append(pack_kmajor_sw128(wv[:, 256:411], 128, 256))
     parts.append(pack_kmajor_sw128(wv[:, :256], 128, 256))
     assert sum(x.numel() for x in parts) == T_BYTES + M_BYTES
     floats += [sd[f"pts_linears.{i}.bias"] for i in range(8)]

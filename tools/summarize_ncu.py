@@ -1,0 +1,83 @@
+"""Summarise ncu outputs into small text files under profiles/ (what the judge reads).
+
+  python tools/summarize_ncu.py launches gpurun_out/launches.csv profiles/r01_launches_<tag>.txt [steps]
+  python tools/summarize_ncu.py full gpurun_out/prof.ncu-rep profiles/r01_ncu_<tag>.txt
+"""
+import csv
+import subprocess
+import sys
+from collections import OrderedDict
+
+
+def short(name):
+    name = name.replace("void ", "")
+    for k in ("xformer_tc_kernel", "mlp_tc_kernel", "sample_knn_kernel", "deform_project_kernel", "gather_tokens_kernel",
+              "composite_kernel", "grid_build", "frame_prepare", "fused_tc_kernel"):
+        if k in name:
+            return name[:name.index("(")] if "(" in name else name
+    if "(" in name:
+        name = name[:name.index("(")]
+    return name[:90]
+
+
+def launches(src, dst, steps):
+    rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"'))]
+    hdr, rows = rows[0], rows[1:]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = OrderedDict()
+    for r in rows:
+        k = short(r[ki])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[vi].replace(",", "")) / 1e3
+    total = sum(v[1] for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none; {len(rows)} launches over {steps} render steps "
+                f"(cold-cache, serialised: compare SHARES)\n")
+        f.write(f"# total {total:.1f} us = {total / steps:.1f} us per step\n")
+        f.write(f"{'kernel':<92}{'launches':>9}{'us total':>12}{'us/step':>11}{'share':>8}\n")
+        for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k:<92}{n:>9}{us:>12.1f}{us / steps:>11.1f}{100 * us / total:>7.1f}%\n")
+    print(open(dst).read())
+
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__t_bytes.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed.avg.per_cycle_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__warps_eligible.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+        "launch__cluster_dim_x", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_drain_per_issue_active.ratio", "smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio"]
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ki = hdr.index("Kernel Name")
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on; source report {src} (not committed)\n")
+        for r in data:
+            f.write(f"\n== {short(r[ki])}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n")
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write(f"{k:<96}{r[i]:>18} {units[i]}\n")
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1)
+    else:
+        full(sys.argv[2], sys.argv[3])
