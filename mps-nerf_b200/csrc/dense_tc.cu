@@ -91,6 +91,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, z * p, hx);
 }
 
+// GELU on two values at once in half precision: 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with the hardware
+// tanh.approx.f16x2 (one MUFU op per pair).  The three coefficients are a minimax fit of the erf form
+// (max |error| 2.5e-5 on the real line, 20x tighter than the usual two-term tanh form); the f16 arithmetic
+// of the tanh argument adds < 4e-4 absolute, below the bf16 rounding (4e-3) of the operand this feeds.  x^2 is clamped at 36:
+// beyond |x| = 6 the polynomial would turn around, tanh is +-1 there anyway.  Returns bf16 x2.
+__device__ __forceinline__ uint32_t gelu_pair_bf16(float x0, float x1) {
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(36.0f));
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.51516790e-04f), __float2half2_rn(3.70056460e-02f));
+  p = __hfma2(x2, p, __float2half2_rn(7.97507884e-01f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  const uint32_t ui = *reinterpret_cast<const uint32_t*>(&u);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&ti));
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;          // the linear part stays in fp32
+  return pack_bf16x2(fmaf(h0, t.x, h0), fmaf(h1, t.y, h1));
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -199,6 +218,32 @@ struct RingConsumer {
   __device__ __forceinline__ void advance() { if (++slot == kSlots) { slot = 0; phase ^= 1; } }
 };
 
+// Both fused kernels run 640 threads = 5 warpgroups: four epilogue warpgroups (16 warps, four
+// threads per row: thread (r = tid & 127, q = tid >> 7) owns a quarter of the row's columns; raised to
+// 104 registers) and one holding the producer warp (16), the MMA warp (17) and two idle warps (lowered
+// to 40), via setmaxnreg.  16 epilogue warps instead of 8: the epilogues are latency bound (issue
+// slots 30 % busy with 2 warps per scheduler), and per-thread state halves.
+constexpr int kFThreads = 640, kFEpiThreads = 512, kFProdWarp = 16, kFMmaWarp = 17;
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+__device__ __forceinline__ void f_epi_bar() { named_bar_sync(1, kFEpiThreads); }
+// the four threads of a row live in warps w, w + 4, w + 8, w + 12: barrier among those 128 threads
+__device__ __forceinline__ void f_row_bar(int warp) { named_bar_sync(2 + (warp & 3), 128); }
+
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ------------------------------------------------------------------------------------------
 // T: cross-view transformer.  Tile = ppt = 128 / V points, row r = (point r / V, token r % V).
 // TMEM columns:
@@ -211,9 +256,9 @@ struct RingConsumer {
 constexpr uint32_t kT_ColX = 0, kT_ColR = 160, kT_ColY = 352, kT_ColO = 432;
 constexpr uint32_t kT_KX = 0;                      // k of the current head, fp32 [128][64], rows of 256 B, unit-swizzled
 constexpr uint32_t kT_VX = kT_KX + 32768;          // v of the current head, fp16 [128][64], rows of 128 B, unit-swizzled
-constexpr uint32_t kT_PD = kT_VX + 16384;          // partial q.k dots  float[2][128][4]
-constexpr uint32_t kT_LS = kT_PD + 4096;           // LayerNorm partial sums float[2][2][128]
-constexpr uint32_t kT_RING = kT_LS + 2048;         // 1024-aligned: 32768 + 16384 + 4096 + 2048 = 55296 = 54 * 1024
+constexpr uint32_t kT_PD = kT_VX + 16384;          // partial q.k dots  float[4][128][4]
+constexpr uint32_t kT_LS = kT_PD + 8192;           // LayerNorm partial sums float[2][4][128]
+constexpr uint32_t kT_RING = kT_LS + 4096;         // 1024-aligned: 32768 + 16384 + 8192 + 4096 = 61440 = 60 * 1024
 constexpr int kT_Slots = 6;
 constexpr uint32_t kT_SlotBytes = kQkvChunk;
 constexpr uint32_t kT_FP = kT_RING + kT_Slots * kT_SlotBytes;
@@ -233,38 +278,39 @@ struct TArgs {
   int prof;
 };
 
-// LayerNorm over the 155 real columns of a row whose 160 columns are split between two threads
-// (this thread: x[0..80) = columns 80*half ..; real columns: 80 or 75), result bf16-packed -> YT.
-// gamma/beta are zero in the 5 pad columns, so the pad of the operand is exactly zero.
-__device__ __forceinline__ void ln_to_tmem(float (&x)[80], const float* __restrict__ pend,
+// LayerNorm over the 155 real columns of a row whose 160 columns are split between four threads
+// (this thread: x[0..40) = columns 40 q ..; real columns: 40 or 35), result bf16-packed -> YT.
+// gamma/beta are zero in the 5 pad columns, so the pad of the operand is exactly zero.  Two passes
+// (mean, then centred variance) like the reference's nn.LayerNorm; the partial sums of a row meet in LS.
+__device__ __forceinline__ void ln_to_tmem(float (&x)[40], const float* __restrict__ pend,
                                            const float* __restrict__ g, const float* __restrict__ b, float* LS,
-                                           int r, int half, uint32_t tl) {
-  const int nreal = half ? 75 : 80;
+                                           int r, int q, int warp, uint32_t tl) {
+  const int nreal = (q == 3) ? 35 : 40;
   if (pend) {
-    const float4* p4 = reinterpret_cast<const float4*>(pend + 80 * half);
+    const float4* p4 = reinterpret_cast<const float4*>(pend + 40 * q);
 #pragma unroll
-    for (int c = 0; c < 20; ++c) {
+    for (int c = 0; c < 10; ++c) {
       const float4 t = p4[c];
       x[4 * c] += t.x; x[4 * c + 1] += t.y; x[4 * c + 2] += t.z; x[4 * c + 3] += t.w;
     }
   }
   float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 80; ++c) if (c < nreal) s[c & 3] += x[c];
-  LS[half * 128 + r] = (s[0] + s[1]) + (s[2] + s[3]);
-  epi_bar();
-  const float mean = (LS[r] + LS[128 + r]) * (1.0f / 155.0f);
+  for (int c = 0; c < 40; ++c) if (c < nreal) s[c & 3] += x[c];
+  LS[q * 128 + r] = (s[0] + s[1]) + (s[2] + s[3]);
+  f_row_bar(warp);
+  const float mean = ((LS[r] + LS[128 + r]) + (LS[256 + r] + LS[384 + r])) * (1.0f / 155.0f);
   float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 80; ++c) if (c < nreal) { const float d = x[c] - mean; v[c & 3] = fmaf(d, d, v[c & 3]); }
-  LS[256 + half * 128 + r] = (v[0] + v[1]) + (v[2] + v[3]);
-  epi_bar();
-  const float rstd = rsqrtf((LS[256 + r] + LS[384 + r]) * (1.0f / 155.0f) + 1e-5f);
-  const float4* g4 = reinterpret_cast<const float4*>(g + 80 * half);
-  const float4* b4 = reinterpret_cast<const float4*>(b + 80 * half);
-  uint32_t pk[40];
+  for (int c = 0; c < 40; ++c) if (c < nreal) { const float d = x[c] - mean; v[c & 3] = fmaf(d, d, v[c & 3]); }
+  LS[512 + q * 128 + r] = (v[0] + v[1]) + (v[2] + v[3]);
+  f_row_bar(warp);
+  const float rstd = rsqrtf(((LS[512 + r] + LS[640 + r]) + (LS[768 + r] + LS[896 + r])) * (1.0f / 155.0f) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g + 40 * q);
+  const float4* b4 = reinterpret_cast<const float4*>(b + 40 * q);
+  uint32_t pk[20];
 #pragma unroll
-  for (int c = 0; c < 20; ++c) {
+  for (int c = 0; c < 10; ++c) {
     const float4 gg = g4[c], bb = b4[c];
     const float y0 = fmaf((x[4 * c] - mean) * rstd, gg.x, bb.x), y1 = fmaf((x[4 * c + 1] - mean) * rstd, gg.y, bb.y);
     const float y2 = fmaf((x[4 * c + 2] - mean) * rstd, gg.z, bb.z), y3 = fmaf((x[4 * c + 3] - mean) * rstd, gg.w, bb.w);
@@ -272,14 +318,13 @@ __device__ __forceinline__ void ln_to_tmem(float (&x)[80], const float* __restri
     pk[2 * c + 1] = pack_bf16x2(y2, y3);
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i)      // every TMEM access is aligned to its own width (here 8 columns)
-    tmem_st_x8(tl + kT_ColY + 40 * half + 8 * i, *reinterpret_cast<const uint32_t(*)[8]>(&pk[8 * i]));
+  for (int i = 0; i < 5; ++i) tmem_st_x4(tl + kT_ColY + 20 * q + 4 * i, &pk[4 * i]);   // every TMEM access aligned to its own width
   tmem_st_wait();
 }
 
-__device__ __forceinline__ void load_x80(uint32_t taddr, float (&x)[80]) {
+__device__ __forceinline__ void load_x40(uint32_t taddr, float (&x)[40]) {
 #pragma unroll
-  for (int i = 0; i < 5; ++i) tmem_ld_x16(taddr + 16 * i, *reinterpret_cast<float(*)[16]>(&x[16 * i]));
+  for (int i = 0; i < 5; ++i) tmem_ld_x8(taddr + 8 * i, &x[8 * i]);
   tmem_ld_wait();
 }
 
@@ -287,8 +332,8 @@ __device__ __forceinline__ void load_x80(uint32_t taddr, float (&x)[80]) {
 // share the weight stream: CTA j loads slice j of every chunk and multicasts it to all of them, so
 // each chunk crosses L2 -> SM once per cluster.  A ring slot is reused only after the MMA warps of
 // *all* kC CTAs have released it (empty barriers count kC arrivals, delivered by multicast commits).
-template <int kV, int kC>
-__global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a) {
+template <int kV, int kC, bool kProf>
+__global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Pipe* pipe = reinterpret_cast<Pipe*>(smem + kT_PIPE);
   float* FP = reinterpret_cast<float*>(smem + kT_FP);
@@ -301,15 +346,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
 
   if (tid == 0) {
     for (int i = 0; i < kT_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], kC); }
-    mbar_init(&pipe->a_bar[0], kEpiThreads);
+    mbar_init(&pipe->a_bar[0], kFEpiThreads);
     mbar_init(&pipe->d_bar[0], 1);
-    mbar_init(&pipe->r_bar, kEpiThreads);
+    mbar_init(&pipe->r_bar, kFEpiThreads);
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
+  if (warp == kFMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
   {
     const float* src = reinterpret_cast<const float*>(a.blob + kFloatOff);
-    for (int i = tid; i < kTFloats; i += kTcThreads) FP[i] = src[i];
+    for (int i = tid; i < kTFloats; i += kFThreads) FP[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -317,76 +362,91 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
   tc_fence_after();
   const uint32_t tm = pipe->tmem_base;
 
-  if (warp == kProdWarp) {
-    // ================= weight producer =================
-    if (lane == 0) {
-      Producer<kT_Slots, kT_SlotBytes, kC> P{pipe, smem + kT_RING, crank};
-      P.pf = Prof{a.prof != 0, 0};
-      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {   // cluster-uniform trip count
-        for (int l = 0; l < 2; ++l) {
-          const uint8_t* src = a.blob + (size_t)l * kTLayerBytes;
-          for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);                                   // qkv_0
-          for (int h = 0; h < 3; ++h) { for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk); P.push(src, kWoChunk); }   // qkv_{h+1}, Wo_h
-          P.push(src, kWoChunk);                                                                 // Wo_3
-          for (int c = 0; c < 3; ++c) P.push(src, kW1Chunk);
-          for (int c = 0; c < 2; ++c) P.push(src, kW2Chunk);
-        }
+  if (warp >= 16) {
+    reg_dec<40>();           // fifth warpgroup: producer, MMA issuer, two idle warps
+  if (warp == kFProdWarp) {
+    // ================= weight producer (whole warp converged, one elected lane issues) =================
+    RingProducer<kT_Slots, kT_SlotBytes, kC> P{pipe, smem + kT_RING, crank};
+    P.pf = Prof{kProf && a.prof == 1 && lane == 0, 0};
+    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {   // cluster-uniform trip count
+#pragma unroll 1
+      for (int l = 0; l < 2; ++l) {
+        const uint8_t* src = a.blob + (size_t)l * kTLayerBytes;
+        for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);                                   // qkv_0
+#pragma unroll 1
+        for (int h = 0; h < 3; ++h) { for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk); P.push(src, kWoChunk); }   // qkv_{h+1}, Wo_h
+        P.push(src, kWoChunk);                                                                 // Wo_3
+        for (int c = 0; c < 3; ++c) P.push(src, kW1Chunk);
+        for (int c = 0; c < 2; ++c) P.push(src, kW2Chunk);
       }
-      if (a.prof) atomicAdd(&g_prof[0][6], (unsigned long long)P.acc_e);
     }
-  } else if (warp == kMmaWarp) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      Consumer<kT_Slots, kT_SlotBytes, kC> Cn{pipe, smem_u32(smem + kT_RING)};
-      Cn.pf = Prof{a.prof != 0, 0};
-      uint32_t rr = 0;
-      const long long t_begin = clock64();
-      // A (TMEM, `ksteps` K=16 steps starting at column acol) x weight chunks with N rows -> D column dcol
-      auto gemm = [&](uint32_t dcol, uint32_t acol, int ksteps, int N, bool accumulate) {
-        const uint32_t idesc = instr_desc_bf16(N);
-        for (int k0 = 0; k0 < ksteps; k0 += 4) {
-          const uint32_t b0 = Cn.slot_wait();
+    if (P.pf.on) atomicAdd(&g_prof[0][6], (unsigned long long)P.acc_e);
+  } else if (warp == kFMmaWarp) {
+    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+    RingConsumer<kT_Slots, kT_SlotBytes, kC> Cn{pipe, smem_u32(smem + kT_RING)};
+    Prof pf{kProf && a.prof == 1 && lane == 0, 0};
+    Cn.pf = pf;
+    long long acc_a = 0;
+    uint32_t g = 0, rr = 0;
+    const long long t_begin = clock64();
+    auto wait_a = [&]() { pf.start(); mbar_wait(&pipe->a_bar[0], g & 1); pf.stop(acc_a); tc_fence_after(); };
+    auto done = [&]() { if (elect_one()) mma_commit(&pipe->d_bar[0]); __syncwarp(); ++g; };
+    // A (TMEM, kSteps K=16 steps starting at column acol) x weight chunks with kN rows -> D column dcol.
+    // One ring slot per 64 K columns: the barrier probe of a chunk hides behind the queued MMAs of the previous one.
+    auto gemm = [&](auto ksteps_c, auto n_c, uint32_t dcol, uint32_t acol, bool accumulate) {
+      constexpr int kSteps = decltype(ksteps_c)::value, kN = decltype(n_c)::value;
+      constexpr uint32_t idesc = instr_desc_bf16(kN);
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const int ks = k0 + k4;
-            if (ks < ksteps)
-              mma_bf16_ts(tm + dcol, tm + acol + ks * 8, smem_desc_sw128(b0 + k4 * 32), idesc, (accumulate || ks > 0) ? 1u : 0u);
-          }
-          Cn.slot_free();
+      for (int k0 = 0; k0 < kSteps; k0 += 4) {
+        const uint64_t bdesc = smem_desc_sw128(Cn.acquire());
+        if (elect_one()) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            if (k0 + k4 < kSteps)
+              mma_bf16_ts(tm + dcol, tm + acol + (k0 + k4) * 8, bdesc + (uint64_t)(k4 * 2), idesc, (accumulate || k0 + k4 > 0) ? 1u : 0u);
+          Cn.release_elected();
         }
-      };
-      for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
-        for (int l = 0; l < 2; ++l) {
-          Cn.wait_a(); gemm(kT_ColR, kT_ColY, 10, 192, false); Cn.done();           // q|k|v of head 0
-          for (int h = 0; h < 4; ++h) {
-            if (h < 3) {                                                             // R copied out by the epilogue:
-              mbar_wait(&pipe->r_bar, rr & 1); ++rr; tc_fence_after();               // q|k|v of head h+1 overlaps the
-              gemm(kT_ColR, kT_ColY, 10, 192, false);                                // attention math of head h
-            }
-            Cn.wait_a();
-            gemm(kT_ColX, kT_ColO, 4, 160, true);                                    // x += o_h Wo_h^T
-            Cn.done();
-          }
-          Cn.wait_a(); gemm(kT_ColR, kT_ColY, 10, 128, false); Cn.done();            // FF hidden
-          Cn.wait_a(); gemm(kT_ColX, kT_ColO, 8, 160, true); Cn.done();              // x += gelu(.) W2^T
-        }
+        __syncwarp();
+        Cn.advance();
       }
-      if (a.prof) {
-        atomicAdd(&g_prof[0][3], (unsigned long long)Cn.acc_a);
-        atomicAdd(&g_prof[0][4], (unsigned long long)Cn.acc_w);
-        atomicAdd(&g_prof[0][5], (unsigned long long)(clock64() - t_begin));
+    };
+    using K10 = std::integral_constant<int, 10>; using K4 = std::integral_constant<int, 4>; using K8 = std::integral_constant<int, 8>;
+    using N192 = std::integral_constant<int, 192>; using N160 = std::integral_constant<int, 160>; using N128 = std::integral_constant<int, 128>;
+    for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
+#pragma unroll 1
+      for (int l = 0; l < 2; ++l) {
+        wait_a(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); done();           // q|k|v of head 0
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          if (h < 3) {                                                             // R copied out by the epilogue:
+            mbar_wait(&pipe->r_bar, rr & 1); ++rr; tc_fence_after();               // q|k|v of head h+1 overlaps the
+            gemm(K10{}, N192{}, kT_ColR, kT_ColY, false);                          // attention math of head h
+          }
+          wait_a();
+          gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                              // x += o_h Wo_h^T
+          done();
+        }
+        wait_a(); gemm(K10{}, N128{}, kT_ColR, kT_ColY, false); done();            // FF hidden
+        wait_a(); gemm(K8{}, N160{}, kT_ColX, kT_ColO, true); done();              // x += gelu(.) W2^T
       }
     }
+    if (pf.on) {
+      atomicAdd(&g_prof[0][3], (unsigned long long)acc_a);
+      atomicAdd(&g_prof[0][4], (unsigned long long)Cn.acc_w);
+      atomicAdd(&g_prof[0][5], (unsigned long long)(clock64() - t_begin));
+    }
+  }
   } else {
     // ================= epilogue warps =================
-    const int r = tid & 127, half = tid >> 7;
+    reg_inc<104>();
+    const int r = tid & 127, q = tid >> 7;
     uint8_t* KX = smem + kT_KX;
     uint8_t* VX = smem + kT_VX;
     float* PD = reinterpret_cast<float*>(smem + kT_PD);
     float* LS = reinterpret_cast<float*>(smem + kT_LS);
     const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t g = 0;
-    Prof pf{a.prof != 0 && tid == 0, 0};
+    Prof pf{kProf && a.prof == 1 && tid == 0, 0};
     long long acc_d = 0, acc_tl = 0, n_tiles = 0;
     long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // publish, bar1, dots, bar2, softmax+o, LN2, GELU, LN1/final
     const long long t_begin = clock64();
@@ -394,6 +454,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
     auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar[0], g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
     constexpr int rows = ppt * V;
     const int p0 = (r < rows) ? (r / V) * V : 0;      // first row of this row's point (attention partners)
+    float4 xn[10];                                     // this thread's 40 token columns of the next tile
+    auto load_tokens = [&](int64_t tile) {
+      const int64_t row = min((tile * ppt + min(r, rows - 1) / V) * V + r % V, a.count * V - 1);
+      const float4* src = reinterpret_cast<const float4*>(a.tokens + row * (int64_t)a.ld + 40 * q);
+#pragma unroll
+      for (int c = 0; c < 10; ++c) xn[c] = __ldg(src + c);
+    };
+    bool first = true;
 
     for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
       const int64_t tile = tbase + crank;              // tile >= ntiles: all rows invalid
@@ -401,118 +469,123 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
       const int tok = r % V;
       const bool valid = (r < rows) && (pnt < a.count);
       {
-        // ---- tile load: tokens -> X (TMEM), LN1 of layer 0 -> YT
+        // ---- tile load: tokens -> X (TMEM), LN1 of layer 0 -> YT.  The tokens were fetched into xn while
+        // the previous tile's last GEMM ran (rows past the end are clamped: rows are independent and
+        // never written); only the first tile pays the global latency here.
         pf.start();
-        float x[80];
-        if (valid) {
-          const float4* src = reinterpret_cast<const float4*>(a.tokens + (pnt * V + tok) * (int64_t)a.ld + 80 * half);
+        if (first) { load_tokens(tile); first = false; }
+        float x[40];
 #pragma unroll
-          for (int c = 0; c < 20; ++c) {
-            const float4 t = __ldg(src + c);
-            x[4 * c] = t.x; x[4 * c + 1] = t.y; x[4 * c + 2] = t.z; x[4 * c + 3] = t.w;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 80; ++c) x[c] = 0.f;
-        }
+        for (int c = 0; c < 10; ++c) { x[4 * c] = xn[c].x; x[4 * c + 1] = xn[c].y; x[4 * c + 2] = xn[c].z; x[4 * c + 3] = xn[c].w; }
         {
-          uint32_t xb[80];
+          uint32_t xb[40];
 #pragma unroll
-          for (int c = 0; c < 80; ++c) xb[c] = __float_as_uint(x[c]);
+          for (int c = 0; c < 40; ++c) xb[c] = __float_as_uint(x[c]);
 #pragma unroll
-          for (int i = 0; i < 5; ++i) tmem_st_u16(tl + kT_ColX + 80 * half + 16 * i, xb + 16 * i);   // 16-aligned
+          for (int i = 0; i < 5; ++i) tmem_st_x8(tl + kT_ColX + 40 * q + 8 * i, *reinterpret_cast<const uint32_t(*)[8]>(&xb[8 * i]));
         }
-        ln_to_tmem(x, nullptr, FP, FP + 160, LS, r, half, tl);
+        ln_to_tmem(x, nullptr, FP, FP + 160, LS, r, q, warp, tl);
         pf.stop(acc_tl);
         hand_over();
       }
+#pragma unroll 1
       for (int l = 0; l < 2; ++l) {
         const float* fp = FP + l * kTLayerFloats;   // ln1_g ln1_b pend_in ln2_g ln2_b pend_mid b1
+#pragma unroll 1
         for (int h = 0; h < 4; ++h) {
           wait_d();
           pf.start();
-          // ---- attention of head h (lib/transformer.py:59-71): R = [q | k | v], 64 columns each.
-          // half 0 publishes k as fp32, half 1 publishes v as fp16 (unit-swizzled rows)
-          {
-            float t[64];
-            tmem_ld_x32(tl + kT_ColR + 64 + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
-            tmem_ld_x32(tl + kT_ColR + 64 + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
-            tmem_ld_wait();
-            if (half == 0) {
-              uint8_t* dst = KX + r * 256;
-#pragma unroll
-              for (int u = 0; u < 16; ++u)
-                *reinterpret_cast<float4*>(dst + ((u ^ (r & 15)) << 4)) = make_float4(t[4 * u], t[4 * u + 1], t[4 * u + 2], t[4 * u + 3]);
-            } else {
-              uint8_t* dst = VX + r * 128;
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const uint4 pk = make_uint4(pack_h2(t[8 * u], t[8 * u + 1]), pack_h2(t[8 * u + 2], t[8 * u + 3]),
-                                            pack_h2(t[8 * u + 4], t[8 * u + 5]), pack_h2(t[8 * u + 6], t[8 * u + 7]));
-                *reinterpret_cast<uint4*>(dst + ((u ^ (r & 7)) << 4)) = pk;
-              }
-            }
-          }
-          float q[32];
-          tmem_ld_x32(tl + kT_ColR + 32 * half, q);
+          // ---- attention of head h (lib/transformer.py:59-71): R = [q | k | v], 64 columns each; this
+          // thread owns head dims [16 q, 16 q + 16) of its row.  It keeps its own q, k, v slices in
+          // registers (fp32) and publishes k (fp32) and v (fp16) in unit-swizzled rows for the V - 1
+          // partner rows of its point; nobody reads back its own row.  Softmax and the weighted sum are symmetric in the key order, so
+          // keys are visited as (self, partner 1, ..) -- no per-lane key index is needed.
+          float qv[16], kk[16], vv[16];
+          tmem_ld_x16(tl + kT_ColR + 64 + 16 * q, kk);
+          tmem_ld_x16(tl + kT_ColR + 128 + 16 * q, vv);
+          tmem_ld_x16(tl + kT_ColR + 16 * q, qv);
           tmem_ld_wait();
           if (h < 3) { tc_fence_before(); mbar_arrive(&pipe->r_bar); }   // R is free: the next head's q|k|v may land
-          pf.stop(sec[0]);
-          epi_bar();
-          pf.stop(sec[1]);
-          // partial dots over this thread's 32 of the 64 head dims (fp32, no conversions)
+          {
+            uint8_t* kd = KX + r * 256;
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            const int rj = p0 + j;
-            const uint8_t* src = KX + rj * 256;
-            float4 kk[8];
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<float4*>(kd + (((4 * q + u) ^ (r & 15)) << 4)) = make_float4(kk[4 * u], kk[4 * u + 1], kk[4 * u + 2], kk[4 * u + 3]);
+            uint8_t* vd = VX + r * 128;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)      // all loads of the row first: one exposed smem latency per row
-              kk[u] = *reinterpret_cast<const float4*>(src + (((8 * half + u) ^ (rj & 15)) << 4));
+            for (int u = 0; u < 2; ++u)
+              *reinterpret_cast<uint4*>(vd + (((2 * q + u) ^ (r & 7)) << 4)) =
+                  make_uint4(pack_h2(vv[8 * u], vv[8 * u + 1]), pack_h2(vv[8 * u + 2], vv[8 * u + 3]),
+                             pack_h2(vv[8 * u + 4], vv[8 * u + 5]), pack_h2(vv[8 * u + 6], vv[8 * u + 7]));
+          }
+          {   // own key while the partners' rows are still being published
             float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              d[0] = fmaf(q[4 * u], kk[u].x, d[0]); d[1] = fmaf(q[4 * u + 1], kk[u].y, d[1]);
-              d[2] = fmaf(q[4 * u + 2], kk[u].z, d[2]); d[3] = fmaf(q[4 * u + 3], kk[u].w, d[3]);
+            for (int u = 0; u < 4; ++u) {
+              d[0] = fmaf(qv[4 * u], kk[4 * u], d[0]); d[1] = fmaf(qv[4 * u + 1], kk[4 * u + 1], d[1]);
+              d[2] = fmaf(qv[4 * u + 2], kk[4 * u + 2], d[2]); d[3] = fmaf(qv[4 * u + 3], kk[4 * u + 3], d[3]);
             }
-            PD[(half * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
+            PD[(q * 128 + r) * 4] = (d[0] + d[1]) + (d[2] + d[3]);
+          }
+          pf.stop(sec[0]);
+          f_epi_bar();            // a point's rows may sit in different lane quarters: CTA-wide
+          pf.stop(sec[1]);
+          // partial dots with the partner keys over this thread's 16 of the 64 head dims (fp32 accumulation)
+#pragma unroll
+          for (int j = 1; j < V; ++j) {
+            const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
+            const uint8_t* src = KX + rj * 256;
+            float4 kp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)      // all loads of the row first: one exposed smem latency per row
+              kp[u] = *reinterpret_cast<const float4*>(src + (((4 * q + u) ^ (rj & 15)) << 4));
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              d[0] = fmaf(qv[4 * u], kp[u].x, d[0]); d[1] = fmaf(qv[4 * u + 1], kp[u].y, d[1]);
+              d[2] = fmaf(qv[4 * u + 2], kp[u].z, d[2]); d[3] = fmaf(qv[4 * u + 3], kp[u].w, d[3]);
+            }
+            PD[(q * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
           }
           pf.stop(sec[2]);
-          epi_bar();
+          f_row_bar(warp);
           pf.stop(sec[3]);
           float w[V];
           float mx = -1e30f;
 #pragma unroll
           for (int j = 0; j < V; ++j) {
-            w[j] = (PD[r * 4 + j] + PD[(128 + r) * 4 + j]) * 0.125f;      // dim_head ** -0.5
+            w[j] = ((PD[r * 4 + j] + PD[(128 + r) * 4 + j]) + (PD[(256 + r) * 4 + j] + PD[(384 + r) * 4 + j])) * 0.125f;   // dim_head ** -0.5
             mx = fmaxf(mx, w[j]);
           }
           float den = 0.f;
 #pragma unroll
           for (int j = 0; j < V; ++j) { w[j] = __expf(w[j] - mx); den += w[j]; }
           const float inv = 1.0f / den;
-          // o = sum_j softmax_j * v_j over this thread's 32 dims, accumulated as half2 (3 terms;
+          // o = sum_j softmax_j * v_j over this thread's 16 dims, accumulated as half2 (V terms;
           // the result is rounded to bf16 for the out-projection anyway)
-          __half2 oh[16];
+          __half2 oh[8];
+          {
+            const __half2 w0 = __float2half2_rn(w[0] * inv);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) oh[i] = __float2half2_rn(0.f);
+            for (int i = 0; i < 8; ++i) oh[i] = __hmul2(w0, __floats2half2_rn(vv[2 * i], vv[2 * i + 1]));
+          }
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            const int rj = p0 + j;
+          for (int j = 1; j < V; ++j) {
+            const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
             const __half2 wj = __float2half2_rn(w[j] * inv);
             const uint8_t* src = VX + rj * 128;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint4 pkv = *reinterpret_cast<const uint4*>(src + (((4 * half + u) ^ (rj & 7)) << 4));
+            for (int u = 0; u < 2; ++u) {
+              const uint4 pkv = *reinterpret_cast<const uint4*>(src + (((2 * q + u) ^ (rj & 7)) << 4));
               const __half2* h2 = reinterpret_cast<const __half2*>(&pkv);
 #pragma unroll
               for (int i = 0; i < 4; ++i) oh[4 * u + i] = __hfma2(wj, h2[i], oh[4 * u + i]);
             }
           }
-          uint32_t pk[16];
+          uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(oh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
-          tmem_st_u16(tl + kT_ColO + 16 * half, pk);
+          for (int i = 0; i < 8; ++i) { const float2 f = __half22float2(oh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
+          tmem_st_x8(tl + kT_ColO + 8 * q, pk);
           tmem_st_wait();
           pf.stop(sec[4]);
           hand_over();
@@ -521,9 +594,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
           // ---- x (+ deferred biases) -> LN2 -> YT
           wait_d();
           pf.start();
-          float x[80];
-          load_x80(tl + kT_ColX + 80 * half, x);
-          ln_to_tmem(x, fp + 800, fp + 480, fp + 640, LS, r, half, tl);
+          float x[40];
+          load_x40(tl + kT_ColX + 40 * q, x);
+          ln_to_tmem(x, fp + 800, fp + 480, fp + 640, LS, r, q, warp, tl);
           pf.stop(sec[5]);
           hand_over();
         }
@@ -531,40 +604,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
           // ---- FF hidden: GELU(acc + b1) -> bf16 operand (K = 128 -> 64 packed columns)
           wait_d();
           pf.start();
-          float t[64];
-          tmem_ld_x32(tl + kT_ColR + 64 * half, *reinterpret_cast<float(*)[32]>(&t[0]));
-          tmem_ld_x32(tl + kT_ColR + 64 * half + 32, *reinterpret_cast<float(*)[32]>(&t[32]));
+          float t[32];
+          tmem_ld_x32(tl + kT_ColR + 32 * q, t);
           tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(fp + 960 + 64 * half);
-          uint32_t pk[32];
+          const float4* b4 = reinterpret_cast<const float4*>(fp + 960 + 32 * q);
+          uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const float4 bb = b4[i];
-            pk[2 * i] = pack_bf16x2(gelu_erf(t[4 * i] + bb.x), gelu_erf(t[4 * i + 1] + bb.y));
-            pk[2 * i + 1] = pack_bf16x2(gelu_erf(t[4 * i + 2] + bb.z), gelu_erf(t[4 * i + 3] + bb.w));
+            pk[2 * i] = gelu_pair_bf16(t[4 * i] + bb.x, t[4 * i + 1] + bb.y);
+            pk[2 * i + 1] = gelu_pair_bf16(t[4 * i + 2] + bb.z, t[4 * i + 3] + bb.w);
           }
-          tmem_st_u16(tl + kT_ColO + 32 * half, pk);
-          tmem_st_u16(tl + kT_ColO + 32 * half + 16, pk + 16);
+          tmem_st_u16(tl + kT_ColO + 16 * q, pk);
           tmem_st_wait();
           pf.stop(sec[6]);
           hand_over();
         }
         {
+          if (l == 1 && tbase + ncl * kC < ntiles) load_tokens(tile + ncl * kC);   // in flight during the last GEMM
           wait_d();
           pf.start();
-          float x[80];
-          load_x80(tl + kT_ColX + 80 * half, x);
+          float x[40];
+          load_x40(tl + kT_ColX + 40 * q, x);
           if (l == 0) {
             const float* f1 = FP + kTLayerFloats;        // layer 1: LN1 on x + pend_in
-            ln_to_tmem(x, f1 + 320, f1, f1 + 160, LS, r, half, tl);
+            ln_to_tmem(x, f1 + 320, f1, f1 + 160, LS, r, q, warp, tl);
             pf.stop(sec[7]);
             hand_over();
           } else if (valid && tok < 2) {
             // ---- output tokens 0 (density branch) and 1 (colour branch), lib/skinnning_batch.py:441-442
-            const float4* p4 = reinterpret_cast<const float4*>(FP + 2 * kTLayerFloats + 80 * half);
-            uint4* dst = reinterpret_cast<uint4*>((tok == 0 ? a.tok0 : a.tok1) + pnt * kTokLd + 80 * half);
+            const float4* p4 = reinterpret_cast<const float4*>(FP + 2 * kTLayerFloats + 40 * q);
+            uint4* dst = reinterpret_cast<uint4*>((tok == 0 ? a.tok0 : a.tok1) + pnt * kTokLd + 40 * q);
 #pragma unroll
-            for (int c = 0; c < 10; ++c) {
+            for (int c = 0; c < 5; ++c) {
               const float4 pa = p4[2 * c], pb = p4[2 * c + 1];
               dst[c] = make_uint4(pack_bf16x2(x[8 * c] + pa.x, x[8 * c + 1] + pa.y), pack_bf16x2(x[8 * c + 2] + pa.z, x[8 * c + 3] + pa.w),
                                   pack_bf16x2(x[8 * c + 4] + pb.x, x[8 * c + 5] + pb.y), pack_bf16x2(x[8 * c + 6] + pb.z, x[8 * c + 7] + pb.w));
@@ -585,7 +657,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xformer_tc_kernel(const TArgs a
   tc_fence_before();
   __syncthreads();
   if (kC > 1) cluster_sync_all();      // no CTA may exit while a peer can still multicast into it
-  if (warp == kMmaWarp) tmem_dealloc(tm, 512);
+  if (warp == kFMmaWarp) tmem_dealloc(tm, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -686,15 +758,9 @@ static_assert(sizeof(kMSchedule) / sizeof(uint32_t) == kMScheduleLen + 1, "M sch
 // 640 threads = 5 warpgroups: four epilogue warpgroups (16 warps, four threads per row: thread
 // (r = tid & 127, q = tid >> 7) owns 32 of the 128 columns of an accumulator half; raised to 104
 // registers) and one holding the producer warp, the MMA warp and two idle warps (lowered to 40).
-constexpr int kMThreads = 640, kMEpiThreads = 512, kMProdWarp = 16, kMMmaWarp = 17;
-template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+constexpr int kMThreads = kFThreads, kMEpiThreads = kFEpiThreads, kMProdWarp = kFProdWarp, kMMmaWarp = kFMmaWarp;
 __device__ __forceinline__ void m_epi_bar() { named_bar_sync(1, kMEpiThreads); }
 
-__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
-               : "memory");
-}
 
 // 16 elements (8 packed words) [16 q, 16 q + 16) of the 39-wide positional code [x, sin(f0 x), cos(f0 x), ...],
 // f_k = pi 2^k (run_nerf_helpers.py:337-353); elements >= 39 are zero padding.  One sincospi per
@@ -1231,7 +1297,9 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args);
   };
-#define MPS_T_CASE(V_, C_) if (n_views == V_ && cluster == C_) MPS_CUDA(launch(xformer_tc_kernel<V_, C_>, ta, kT_Smem, t_tiles, C_, kTcThreads));
+#define MPS_T_CASE(V_, C_) if (n_views == V_ && cluster == C_) { \
+    if (prof == 1) MPS_CUDA(launch(xformer_tc_kernel<V_, C_, true>, ta, kT_Smem, t_tiles, C_, kFThreads)); \
+    else MPS_CUDA(launch(xformer_tc_kernel<V_, C_, false>, ta, kT_Smem, t_tiles, C_, kFThreads)); }
   MPS_T_CASE(2, 1) MPS_T_CASE(2, 2) MPS_T_CASE(2, 4)
   MPS_T_CASE(3, 1) MPS_T_CASE(3, 2) MPS_T_CASE(3, 4)
   MPS_T_CASE(4, 1) MPS_T_CASE(4, 2) MPS_T_CASE(4, 4)
