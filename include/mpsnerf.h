@@ -134,6 +134,10 @@ int mpsnerf_deform_project(const int32_t* act_pid, const int32_t* act_idx2, cons
 int mpsnerf_gather_tokens(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
                           const float* latent, const float* img4, float* tokens, int32_t ld,
                           void* stream);
+/* Same lookup, tokens written as IEEE fp16 (count, V, 160), pad = 0, values clamped to +-65504:
+ * the input format of the tensor-core path (mpsnerf_dense_bf16). */
+int mpsnerf_gather_tokens_f16(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
+                              const float* latent, const float* img4, void* tokens, void* stream);
 
 /* ---- K5: cross-view transformer + canonical NeRF MLP -----------------------------------
  * Replaces Transformer.forward (lib/transformer.py:74-86) and the MLP of
@@ -150,7 +154,8 @@ int mpsnerf_dense_fp32(const float* tokens, int32_t ld, const float* xc, int64_t
 /* bf16 tensor-core variant (tcgen05 / TMEM / bulk-async weight streaming).  `packed` is the
  * blob produced by mpsnerf_b200.engine.pack_weights_bf16 (layout: DESIGN.md section 5). */
 size_t mpsnerf_dense_bf16_workspace(int64_t count, int n_views);
-int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* xc, int64_t count,
+/* tokens: fp16 (count, V, 160) as written by mpsnerf_gather_tokens_f16; ld must be 160. */
+int mpsnerf_dense_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
                        int n_views, const void* packed, size_t packed_bytes,
                        const int32_t* act_pid, int64_t first, float* raw, void* workspace,
                        void* stream);

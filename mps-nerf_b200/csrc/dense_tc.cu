@@ -268,7 +268,7 @@ static_assert(kT_RING % 1024 == 0 && kT_SlotBytes % 1024 == 0, "ring slots must 
 static_assert(kT_Smem <= 232448 - 1024, "T kernel shared memory over budget");
 
 struct TArgs {
-  const float* tokens;   // (count, V, ld) fp32
+  const __half* tokens;  // (count, V, 160) fp16
   int ld;
   int64_t count;
   int V;
@@ -454,12 +454,12 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a)
     auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar[0], g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
     constexpr int rows = ppt * V;
     const int p0 = (r < rows) ? (r / V) * V : 0;      // first row of this row's point (attention partners)
-    float4 xn[10];                                     // this thread's 40 token columns of the next tile
+    uint4 xn[5];                                       // this thread's 40 token columns (fp16) of the next tile
     auto load_tokens = [&](int64_t tile) {
       const int64_t row = min((tile * ppt + min(r, rows - 1) / V) * V + r % V, a.count * V - 1);
-      const float4* src = reinterpret_cast<const float4*>(a.tokens + row * (int64_t)a.ld + 40 * q);
+      const uint4* src = reinterpret_cast<const uint4*>(a.tokens + row * (int64_t)kTokLd + 40 * q);
 #pragma unroll
-      for (int c = 0; c < 10; ++c) xn[c] = __ldg(src + c);
+      for (int c = 0; c < 5; ++c) xn[c] = __ldg(src + c);
     };
     bool first = true;
 
@@ -476,7 +476,11 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a)
         if (first) { load_tokens(tile); first = false; }
         float x[40];
 #pragma unroll
-        for (int c = 0; c < 10; ++c) { x[4 * c] = xn[c].x; x[4 * c + 1] = xn[c].y; x[4 * c + 2] = xn[c].z; x[4 * c + 3] = xn[c].w; }
+        for (int c = 0; c < 5; ++c) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&xn[c]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h2[i]); x[8 * c + 2 * i] = f.x; x[8 * c + 2 * i + 1] = f.y; }
+        }
         {
           uint32_t xb[40];
 #pragma unroll
@@ -1247,7 +1251,7 @@ extern "C" size_t mpsnerf_dense_bf16_workspace(int64_t count, int n_views) {
   return 2 * (c * mps::kTokLd * sizeof(__nv_bfloat16) + 256) + 256;
 }
 
-extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* xc, int64_t count,
+extern "C" int mpsnerf_dense_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
                                   int n_views, const void* packed, size_t packed_bytes,
                                   const int32_t* act_pid, int64_t first, float* raw, void* workspace,
                                   void* stream) {
@@ -1273,7 +1277,7 @@ extern "C" int mpsnerf_dense_bf16(const float* tokens, int32_t ld, const float* 
   }
   static int prof = -1;
   if (prof < 0) { const char* e = getenv("MPSNERF_TC_PROF"); prof = e ? atoi(e) : 0; }
-  TArgs ta{tokens, ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof};
+  TArgs ta{static_cast<const __half*>(tokens), ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof};
   MArgs ma{tok0, tok1, xc, count, static_cast<const uint8_t*>(packed), act_pid + first, raw, prof};
   const int ppt = 128 / n_views;
   const int64_t t_tiles = (count + ppt - 1) / ppt, m_tiles = (count + 127) / 128;

@@ -5,6 +5,8 @@
 // align_corners=True, weights from the unclamped corners, indices clamped (border padding).
 // One warp per (point, view): the latent is NHWC so the 128 channels of a tap are one
 // coalesced 512-byte row (a float4 per lane); the 4 taps are independent 128-bit loads.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mps {
@@ -46,9 +48,16 @@ __device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, const 
   return r;
 }
 
+// kHalf: tokens are written as fp16 (row stride ld halfs, ld % 4 == 0) for the tensor-core path, which
+// halves the only large HBM stream of this kernel (the latent taps are L2 hits); values are clamped to the
+// finite fp16 range.  Otherwise fp32 with row stride ld floats.
+template <bool kHalf>
 __global__ void __launch_bounds__(kK4Threads)
 gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */, int V, const mpsnerf_frame* __restrict__ frame,
-                     const float* __restrict__ latent, const float* __restrict__ img4, float* __restrict__ tokens, int ld) {
+                     const float* __restrict__ latent, const float* __restrict__ img4, void* __restrict__ tokens_v, int ld) {
+  float* tokens = static_cast<float*>(tokens_v);
+  __half* tokens_h = static_cast<__half*>(tokens_v);
+  auto clamp_h = [](float x) { return fminf(fmaxf(x, -65504.f), 65504.f); };
   const int img_w = frame->img_w, img_h = frame->img_h, FW = frame->feat_w, FH = frame->feat_h;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * kK4Threads + threadIdx.x) >> 5;
@@ -57,6 +66,7 @@ gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */,
     const int v = (int)(row % V);
     const float u_ = __ldg(&uv[2 * row]), v_ = __ldg(&uv[2 * row + 1]);
     float* out = tokens + row * ld;
+    __half* out_h = tokens_h + row * ld;
     // latent: 128 channels, 4 per lane
     {
       const Taps t = make_taps(u_, v_, img_w, img_h, FW, FH);
@@ -64,7 +74,10 @@ gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */,
       const float4 a = __ldg(base + (size_t)t.o00 * 32), b = __ldg(base + (size_t)t.o01 * 32);
       const float4 c = __ldg(base + (size_t)t.o10 * 32), d = __ldg(base + (size_t)t.o11 * 32);
       const float4 r = lerp4(a, b, c, d, t);
-      if ((ld & 3) == 0) {
+      if (kHalf) {
+        const __half2 lo = __floats2half2_rn(clamp_h(r.x), clamp_h(r.y)), hi = __floats2half2_rn(clamp_h(r.z), clamp_h(r.w));
+        reinterpret_cast<uint2*>(out_h)[lane] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      } else if ((ld & 3) == 0) {
         reinterpret_cast<float4*>(out)[lane] = r;
       } else {
         out[4 * lane] = r.x; out[4 * lane + 1] = r.y; out[4 * lane + 2] = r.z; out[4 * lane + 3] = r.w;
@@ -87,9 +100,9 @@ gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */,
           const float f = 3.14159265358979323846f * (float)(1 << k);
           val = sinf(fmaf(x, f, is_cos ? 1.57079632679489661923f : 0.0f));
         }
-        out[128 + e] = val;
+        if (kHalf) out_h[128 + e] = __float2half_rn(val); else out[128 + e] = val;
       } else if (128 + lane < ld) {
-        out[128 + lane] = 0.f;           // pad columns 155.. (ld <= 160)
+        if (kHalf) out_h[128 + lane] = __float2half_rn(0.f); else out[128 + lane] = 0.f;           // pad columns 155.. (ld <= 160)
       }
     }
   }
@@ -109,8 +122,24 @@ extern "C" int mpsnerf_gather_tokens(const float* uv, int64_t count, int n_views
   const int64_t rows = count * n_views;
   int64_t blocks = (rows * 32 + mps::kK4Threads - 1) / mps::kK4Threads;
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
-  mps::gather_tokens_kernel<<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
+  mps::gather_tokens_kernel<false><<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
       uv, rows, n_views, frame, latent, img4, tokens, ld);
+  MPS_LAUNCH_CHECK();
+  return MPSNERF_OK;
+}
+
+extern "C" int mpsnerf_gather_tokens_f16(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
+                                         const float* latent, const float* img4, void* tokens, void* stream) {
+  MPS_REQUIRE(count >= 0 && n_views >= 1 && n_views <= MPSNERF_MAX_VIEWS);
+  if (count == 0) return MPSNERF_OK;
+  MPS_REQUIRE(uv && frame && latent && img4 && tokens);
+  MPS_REQUIRE((reinterpret_cast<uintptr_t>(latent) & 15) == 0 && (reinterpret_cast<uintptr_t>(img4) & 15) == 0);
+  MPS_REQUIRE((reinterpret_cast<uintptr_t>(tokens) & 15) == 0);
+  const int64_t rows = count * n_views;
+  int64_t blocks = (rows * 32 + mps::kK4Threads - 1) / mps::kK4Threads;
+  if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
+  mps::gather_tokens_kernel<true><<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
+      uv, rows, n_views, frame, latent, img4, tokens, MPSNERF_TOKEN_LD);
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
 }

@@ -238,7 +238,10 @@ class RenderEngine:
             cap = min(slab, n_act)
             xc = self._buf("xc", 12 * cap, dev).view(torch.float32)
             uv = self._buf("uv", 8 * V * cap, dev).view(torch.float32)
-            tokens = self._buf("tokens", 4 * ld * V * cap, dev).view(torch.float32)
+            if self.precision == "fp32":
+                tokens = self._buf("tokens", 4 * ld * V * cap, dev).view(torch.float32)
+            else:       # tensor-core path: fp16 tokens (halves the largest HBM stream of the frame)
+                tokens = self._buf("tokens", 2 * ld * V * cap, dev).view(torch.float16)
             if self.precision == "fp32":
                 wtable, keep = self._weights_fp32()
                 ws = self._buf("dense", lib.mpsnerf_dense_fp32_workspace(cap, V), dev)
@@ -255,8 +258,12 @@ class RenderEngine:
                 _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.grid_tv), _lib.ptr(xc), _lib.ptr(uv), _lib.ptr(ss),
                 _lib.ptr(idx3), _lib.ptr(xw), 1 if all_active else 0, _stream()), "deform_project")
             with self.span("k4_gather"):
-              _lib.check(lib.mpsnerf_gather_tokens(_lib.ptr(uv), cnt, V, _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.latent),
-                                                 _lib.ptr(ctx.img4), _lib.ptr(tokens), ld, _stream()), "gather_tokens")
+              if self.precision == "fp32":
+                _lib.check(lib.mpsnerf_gather_tokens(_lib.ptr(uv), cnt, V, _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.latent),
+                                                     _lib.ptr(ctx.img4), _lib.ptr(tokens), ld, _stream()), "gather_tokens")
+              else:
+                _lib.check(lib.mpsnerf_gather_tokens_f16(_lib.ptr(uv), cnt, V, _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.latent),
+                                                         _lib.ptr(ctx.img4), _lib.ptr(tokens), _stream()), "gather_tokens_f16")
             if self.precision == "fp32":
               with self.span("dense"):
                 _lib.check(lib.mpsnerf_dense_fp32(_lib.ptr(tokens), ld, _lib.ptr(xc), cnt, V, wtable, _lib.ptr(act_pid),
@@ -273,7 +280,7 @@ class RenderEngine:
                 dbg["idx3"].append(idx3[:cnt].clone())
                 dbg["xw"].append(xw[:3 * cnt].reshape(-1, 3).clone())
                 dbg["uv"].append(uv[:2 * V * cnt].reshape(-1, V, 2).clone())
-                dbg["tokens"].append(tokens[:ld * V * cnt].reshape(-1, V, ld).clone())
+                dbg["tokens"].append(tokens[:ld * V * cnt].reshape(-1, V, ld).float())
         if composite and points is None:
             rgb = torch.empty(N, 3, device=dev)
             disp = torch.empty(N, device=dev)

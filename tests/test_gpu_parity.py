@@ -177,7 +177,8 @@ def test_stages_against_oracle(case, precision):
     assert not res["smpl_src_pts"].cpu().numpy()[~mask].any()
     # ---- floating-point stages
     np.testing.assert_allclose(dbg["uv"][order].transpose(1, 0, 2), st["uv"], rtol=1e-5, atol=2e-3)
-    np.testing.assert_allclose(dbg["tokens"][order][..., :155], st["tokens"], atol=2e-4)
+    # the tensor-core path stores the tokens as fp16 (relative rounding 4.9e-4)
+    np.testing.assert_allclose(dbg["tokens"][order][..., :155], st["tokens"], atol=2e-4, rtol=0 if precision == "fp32" else 6e-4)
     assert not dbg["tokens"][..., 155:].any()
     raw = res["raw"].cpu().numpy()
     assert np.all(raw[~mask] == -80.0)
