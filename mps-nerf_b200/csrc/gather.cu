@@ -51,6 +51,11 @@ __device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, const 
 // kHalf: tokens are written as fp16 (row stride ld halfs, ld % 4 == 0) for the tensor-core path, which
 // halves the only large HBM stream of this kernel (the latent taps are L2 hits); values are clamped to the
 // finite fp16 range.  Otherwise fp32 with row stride ld floats.
+//
+// The kernel is issue bound, not bandwidth bound: the tap set-up (two make_taps with their divisions,
+// floors and clamps) is scalar work per row.  A warp therefore takes 32 consecutive rows at a time: lane L
+// sets up row L (taps of the latent, and the complete bilinear RGB lookup), then the warp walks the 32
+// rows, broadcasting one row's taps per step with shuffles and spending its 32 lanes on the 128 channels.
 template <bool kHalf>
 __global__ void __launch_bounds__(kK4Threads)
 gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */, int V, const mpsnerf_frame* __restrict__ frame,
@@ -62,47 +67,54 @@ gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */,
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * kK4Threads + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * kK4Threads) >> 5;
-  for (int64_t row = warp0; row < n_rows; row += nwarps) {
-    const int v = (int)(row % V);
-    const float u_ = __ldg(&uv[2 * row]), v_ = __ldg(&uv[2 * row + 1]);
-    float* out = tokens + row * ld;
-    __half* out_h = tokens_h + row * ld;
-    // latent: 128 channels, 4 per lane
+  // element e of the 27-wide RGB code: e<3 identity; else k=(e-3)/6, ch=(e-3)%3, cos=((e-3)%6)>=3
+  const int e = lane;
+  const int ch = (e < 3) ? e : ((e - 3) % 3);
+  const float freq = (e < 3) ? 0.f : 3.14159265358979323846f * (float)(1 << ((e - 3) / 6));
+  const float phase = (e >= 3 && ((e - 3) % 6) >= 3) ? 1.57079632679489661923f : 0.0f;
+  for (int64_t base = warp0 * 32; base < n_rows; base += nwarps * 32) {
+    // ---- set-up of row base + lane
+    const int64_t my = min(base + lane, n_rows - 1);
+    const int mv = (int)(my % V);
+    const float u_ = __ldg(&uv[2 * my]), v_ = __ldg(&uv[2 * my + 1]);
+    const Taps t = make_taps(u_, v_, img_w, img_h, FW, FH);
+    float4 rgb;
     {
-      const Taps t = make_taps(u_, v_, img_w, img_h, FW, FH);
-      const float4* base = reinterpret_cast<const float4*>(latent + (size_t)v * FH * FW * 128) + lane;
-      const float4 a = __ldg(base + (size_t)t.o00 * 32), b = __ldg(base + (size_t)t.o01 * 32);
-      const float4 c = __ldg(base + (size_t)t.o10 * 32), d = __ldg(base + (size_t)t.o11 * 32);
-      const float4 r = lerp4(a, b, c, d, t);
+      const Taps ti = make_taps(u_, v_, img_w, img_h, img_w, img_h);
+      const float4* ib = reinterpret_cast<const float4*>(img4 + (size_t)mv * img_h * img_w * 4);
+      rgb = lerp4(__ldg(ib + ti.o00), __ldg(ib + ti.o01), __ldg(ib + ti.o10), __ldg(ib + ti.o11), ti);
+    }
+    const int nrow = (int)min((int64_t)32, n_rows - base);
+    // ---- the 32 rows, one per step: latent 128 channels, 4 per lane
+    for (int i = 0; i < nrow; ++i) {
+      const int64_t row = base + i;
+      const int v = (int)(row % V);
+      Taps s;
+      s.o00 = __shfl_sync(0xffffffffu, t.o00, i); s.o01 = __shfl_sync(0xffffffffu, t.o01, i);
+      s.o10 = __shfl_sync(0xffffffffu, t.o10, i); s.o11 = __shfl_sync(0xffffffffu, t.o11, i);
+      s.w00 = __shfl_sync(0xffffffffu, t.w00, i); s.w01 = __shfl_sync(0xffffffffu, t.w01, i);
+      s.w10 = __shfl_sync(0xffffffffu, t.w10, i); s.w11 = __shfl_sync(0xffffffffu, t.w11, i);
+      const float cx = __shfl_sync(0xffffffffu, rgb.x, i), cy = __shfl_sync(0xffffffffu, rgb.y, i), cz = __shfl_sync(0xffffffffu, rgb.z, i);
+      const float4* lb = reinterpret_cast<const float4*>(latent + (size_t)v * FH * FW * 128) + lane;
+      const float4 a = __ldg(lb + (size_t)s.o00 * 32), b = __ldg(lb + (size_t)s.o01 * 32);
+      const float4 c = __ldg(lb + (size_t)s.o10 * 32), d = __ldg(lb + (size_t)s.o11 * 32);
+      const float4 r = lerp4(a, b, c, d, s);
+      // rgb: 27-wide code [x, sin(f0 x), cos(f0 x), ...] with cos as sin(. + fl(pi/2)) (run_nerf_helpers.py:337-353)
+      const float x = ch == 0 ? cx : (ch == 1 ? cy : cz);
+      const float code = (e < 3) ? x : sinf(fmaf(x, freq, phase));
       if (kHalf) {
+        __half* out_h = tokens_h + row * ld;
         const __half2 lo = __floats2half2_rn(clamp_h(r.x), clamp_h(r.y)), hi = __floats2half2_rn(clamp_h(r.z), clamp_h(r.w));
         reinterpret_cast<uint2*>(out_h)[lane] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-      } else if ((ld & 3) == 0) {
-        reinterpret_cast<float4*>(out)[lane] = r;
+        if (128 + lane < ld) out_h[128 + lane] = __float2half_rn(lane < 27 ? code : 0.f);      // pad columns 155.. are zero
       } else {
-        out[4 * lane] = r.x; out[4 * lane + 1] = r.y; out[4 * lane + 2] = r.z; out[4 * lane + 3] = r.w;
-      }
-    }
-    // rgb: 27-wide code [x, sin(f0 x), cos(f0 x), ...] with cos as sin(. + fl(pi/2)) (run_nerf_helpers.py:337-353)
-    {
-      const Taps t = make_taps(u_, v_, img_w, img_h, img_w, img_h);
-      const float4* base = reinterpret_cast<const float4*>(img4 + (size_t)v * img_h * img_w * 4);
-      const float4 r = lerp4(__ldg(base + t.o00), __ldg(base + t.o01), __ldg(base + t.o10), __ldg(base + t.o11), t);
-      // lane l < 27: element e = l; e<3: identity; else k=(e-3)/6, within=(e-3)%6, ch=within%3, cos=within>=3
-      if (lane < 27) {
-        const int e = lane;
-        const int ch = (e < 3) ? e : ((e - 3) % 3);
-        const float x = ch == 0 ? r.x : (ch == 1 ? r.y : r.z);
-        float val = x;
-        if (e >= 3) {
-          const int k = (e - 3) / 6;
-          const bool is_cos = ((e - 3) % 6) >= 3;
-          const float f = 3.14159265358979323846f * (float)(1 << k);
-          val = sinf(fmaf(x, f, is_cos ? 1.57079632679489661923f : 0.0f));
+        float* out = tokens + row * ld;
+        if ((ld & 3) == 0) {
+          reinterpret_cast<float4*>(out)[lane] = r;
+        } else {
+          out[4 * lane] = r.x; out[4 * lane + 1] = r.y; out[4 * lane + 2] = r.z; out[4 * lane + 3] = r.w;
         }
-        if (kHalf) out_h[128 + e] = __float2half_rn(val); else out[128 + e] = val;
-      } else if (128 + lane < ld) {
-        if (kHalf) out_h[128 + lane] = __float2half_rn(0.f); else out[128 + lane] = 0.f;           // pad columns 155.. (ld <= 160)
+        if (128 + lane < ld) out[128 + lane] = lane < 27 ? code : 0.f;
       }
     }
   }
@@ -120,7 +132,7 @@ extern "C" int mpsnerf_gather_tokens(const float* uv, int64_t count, int n_views
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(latent) & 15) == 0 && (reinterpret_cast<uintptr_t>(img4) & 15) == 0);
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(tokens) & 15) == 0);
   const int64_t rows = count * n_views;
-  int64_t blocks = (rows * 32 + mps::kK4Threads - 1) / mps::kK4Threads;
+  int64_t blocks = (rows + mps::kK4Threads - 1) / mps::kK4Threads;      // a warp takes 32 rows per visit
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
   mps::gather_tokens_kernel<false><<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
       uv, rows, n_views, frame, latent, img4, tokens, ld);
@@ -136,7 +148,7 @@ extern "C" int mpsnerf_gather_tokens_f16(const float* uv, int64_t count, int n_v
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(latent) & 15) == 0 && (reinterpret_cast<uintptr_t>(img4) & 15) == 0);
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(tokens) & 15) == 0);
   const int64_t rows = count * n_views;
-  int64_t blocks = (rows * 32 + mps::kK4Threads - 1) / mps::kK4Threads;
+  int64_t blocks = (rows + mps::kK4Threads - 1) / mps::kK4Threads;
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
   mps::gather_tokens_kernel<true><<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
       uv, rows, n_views, frame, latent, img4, tokens, MPSNERF_TOKEN_LD);
