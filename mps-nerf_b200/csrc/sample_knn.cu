@@ -50,13 +50,15 @@ sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const
       if (points != nullptr) {
         px = points[3 * pid]; py = points[3 * pid + 1]; pz = points[3 * pid + 2];
       } else {
-        const int64_t r = pid / S;
-        const int s = (int)(pid - r * S);
-        const float* ray = rays + 8 * r;
-        const float z = sample_z(ray[6], ray[7], t_vals, s, S, u ? u + r * S : nullptr);
-        px = padd(ray[0], pmul(ray[3], z));     // run_nerf_batch.py:424
-        py = padd(ray[1], pmul(ray[4], z));
-        pz = padd(ray[2], pmul(ray[5], z));
+        // P < 2^31 (checked by the host wrapper): 32-bit division instead of the ~100-instruction 64-bit one
+        const uint32_t r = (uint32_t)pid / (uint32_t)S;
+        const int s = (int)((uint32_t)pid - r * (uint32_t)S);
+        const float4 ra = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r);       // o.xyz, d.x
+        const float4 rb = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r + 1);   // d.yz, near, far
+        const float z = sample_z(rb.z, rb.w, t_vals, s, S, u ? u + (size_t)r * S : nullptr);
+        px = padd(ra.x, pmul(ra.w, z));     // run_nerf_batch.py:424
+        py = padd(ra.y, pmul(rb.x, z));
+        pz = padd(ra.z, pmul(rb.y, z));
       }
       const float d0 = psub(px, s_fr[0]), d1 = psub(py, s_fr[1]), d2 = psub(pz, s_fr[2]);
       qx = padd(padd(pmul(d0, s_fr[3]), pmul(d1, s_fr[6])), pmul(d2, s_fr[9]));   // (p-Th)@R, :347
@@ -143,7 +145,7 @@ extern "C" int mpsnerf_sample_knn(const float* rays, int64_t n_rays, int32_t S, 
   MPS_REQUIRE(points != nullptr || (rays != nullptr && t_vals != nullptr));
   MPS_REQUIRE(frame && grid_tp && raw && pts_mask && smpl_query && smpl_src);
   MPS_REQUIRE(act_pid && act_idx2 && act_q && act_count);
-  MPS_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+  MPS_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(rays) & 15) == 0);
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(smpl_query) & 15) == 0 && (reinterpret_cast<uintptr_t>(smpl_src) & 15) == 0);
   int64_t blocks = (P + mps::kK1Threads - 1) / mps::kK1Threads;
   if (blocks > mps::kNumSMs * 8) blocks = mps::kNumSMs * 8;
