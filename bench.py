@@ -192,10 +192,22 @@ def run_ours(a):
     pk = peaks()
     dense_ms = stage_ms.get("dense", float("nan"))
     ach = n_active * FLOP_PER_ACTIVE_POINT / (dense_ms * 1e-3) / 1e12
+    # DRAM bytes of the dense stage (T + M kernels) per step from the committed `ncu --set full` capture
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dense_" + a.precision)
+    # HBM-side figures of the other kernels: algorithmic bytes / CUDA-event time
+    n_pts, V = n_rays * 64, 3
+    alg_bytes = {"k1_sample_knn": n_pts * 44 + n_rays * 32, "k3_deform": n_active * (20 + 48),
+                 "k4_gather": n_active * V * ((4 * 128 + 16) * 4 + 160 * (2 if a.precision == "bf16" else 4)),
+                 "k6_composite": n_rays * (64 * 16 + 52)}
+    kernels = {k: {"bytes": b, "ms": stage_ms.get(k), "achieved_gbs": b / (stage_ms[k] * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": b / (stage_ms[k] * 1e-3) / 1e9 / pk["hbm"]} for k, b in alg_bytes.items() if stage_ms.get(k)}
     roofline = {"bound": "tensor", "kernel": "dense_" + a.precision, "achieved": ach, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["src"] + " sustained bf16",
                 "kernel_ms": dense_ms, "active_points": n_active, "flop_per_active_point": FLOP_PER_ACTIVE_POINT,
-                "stage_ms": stage_ms}
+                "stage_ms": stage_ms, "kernels": kernels, "hbm_peak_gbs": pk["hbm"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

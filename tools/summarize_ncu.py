@@ -76,8 +76,29 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, key):
+    """Sum dram read+write bytes of the fused dense kernels of one capture -> profiles/ncu_traffic.json[key]."""
+    import json, os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for r in data:
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            total += float(r[i].replace(",", "")) * scale[units[i]]
+    d = json.load(open(dst)) if os.path.exists(dst) else {}
+    d[key] = total
+    d[key + "_source"] = os.path.basename(src) + ": " + ", ".join(short(r[hdr.index("Kernel Name")]) for r in data)
+    json.dump(d, open(dst, "w"), indent=1)
+    print(d)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1)
     else:
         full(sys.argv[2], sys.argv[3])
