@@ -44,14 +44,22 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ rays, 
       alpha[k] = 0.f; zs[k] = 0.f; c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < per && s < S) {
         const float4 v = __ldg(raw4 + s);
-        const float z = z_row ? z_row[s] : sample_z(near, far, t_vals, s, S, u_row);
-        float a;
-        if (!occupancy) {
-          const float zn = (s == S - 1) ? 0.f : (z_row ? z_row[s + 1] : sample_z(near, far, t_vals, s + 1, S, u_row));
-          const float dist = (s == S - 1) ? 1e10f : (zn - z);
-          a = 1.f - expf(-softplus_torch(v.w - 1.f) * (dist * dn));
+        float a, z = 0.f;
+        if (!occupancy && v.w == -80.f) {
+          // the fill value of masked-out samples (lib/skinnning_batch.py:493), ~94 % of a frame:
+          // softplus(-81) = 6.6e-36, so alpha = 1 - exp(-6.6e-36 * dist) is exactly 0 for every dist <= 1e10 * |d|
+          // -- a strength reduction, not an approximation; the weight, colour, depth and transmittance terms
+          // vanish with it, so not even z is needed
+          a = 0.f;
         } else {
-          a = wide_sigmoid(v.w);
+          z = z_row ? z_row[s] : sample_z(near, far, t_vals, s, S, u_row);
+          if (!occupancy) {
+            const float zn = (s == S - 1) ? 0.f : (z_row ? z_row[s + 1] : sample_z(near, far, t_vals, s + 1, S, u_row));
+            const float dist = (s == S - 1) ? 1e10f : (zn - z);
+            a = 1.f - expf(-softplus_torch(v.w - 1.f) * (dist * dn));
+          } else {
+            a = wide_sigmoid(v.w);
+          }
         }
         alpha[k] = a; zs[k] = z; c[k] = v;
         prod *= (1.f - a + 1e-10f);
@@ -72,14 +80,16 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ rays, 
       const int s = s0 + k;
       if (k < per && s < S) {
         const float w = alpha[k] * T;
-        sr += w * wide_sigmoid(c[k].x);
-        sg += w * wide_sigmoid(c[k].y);
-        sb += w * wide_sigmoid(c[k].z);
-        sd += w * zs[k];
-        sa += w;
+        if (alpha[k] != 0.f) {          // w == 0 adds nothing and 1 - 0 + 1e-10 == 1 in fp32
+          sr += w * wide_sigmoid(c[k].x);
+          sg += w * wide_sigmoid(c[k].y);
+          sb += w * wide_sigmoid(c[k].z);
+          sd += w * zs[k];
+          sa += w;
+        }
         if (w_out) w_out[r * S + s] = w;
         if (ts_out) ts_out[r * S + s] = T;
-        T *= (1.f - alpha[k] + 1e-10f);
+        if (alpha[k] != 0.f) T *= (1.f - alpha[k] + 1e-10f);
       }
     }
 #pragma unroll

@@ -126,6 +126,8 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, pert
                            occupancy=bool(global_args.occupancy)))
 
     def stack(key, *shape):
+        if B == 1:      # a view: stacking would copy the 0.7 GB of per-sample extras of a full frame once more
+            return per[0][key].reshape(1, C, *shape)
         return torch.stack([r[key].reshape(C, *shape) for r in per], 0)
 
     rgb = stack("rgb_map", 3)
