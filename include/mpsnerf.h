@@ -127,6 +127,15 @@ int mpsnerf_deform_project(const int32_t* act_pid, const int32_t* act_idx2, cons
                            float* smpl_src, int32_t* idx3, float* xw, int identity_canonical,
                            void* stream);
 
+/* ---- K-1: ray generation + box near/far (in front of K1) -------------------------------
+ * Replaces get_rays and get_near_far (lib/if_nerf_data_utils.py:11-25, 55-92), numpy on the CPU in the
+ * reference.  K, R (3x3 row-major), T (3), bounds (2,3 = min,max; widened by 0.01 inside like the
+ * reference) are HOST doubles.  rays8 (H*W, 8) = [o, d, near, far] fp32, pixel (row j, column i) at
+ * j*W + i; rays that do not hit the box exactly twice get near = 0, far = 1 and mask_at_box = 0
+ * (mask_at_box may be NULL). */
+int mpsnerf_gen_rays(const double* K, const double* R, const double* T, const double* bounds, int32_t H,
+                     int32_t W, float* rays8, uint8_t* mask_at_box, void* stream);
+
 /* ---- K4: multiview bilinear feature + RGB lookup, RGB positional code -> tokens --------
  * Replaces SpatialEncoder.index / grid_sample (lib/encoder.py:12-62, 225-253) and the RGB
  * append (lib/skinnning_batch.py:428-435).  latent is NHWC (V,Hf,Wf,128); img is NHWC with
@@ -156,6 +165,17 @@ int mpsnerf_dense_fp32(const float* tokens, int32_t ld, const float* xc, int64_t
 size_t mpsnerf_dense_bf16_workspace(int64_t count, int n_views);
 /* tokens: fp16 (count, V, 160) as written by mpsnerf_gather_tokens_f16; ld must be 160. */
 int mpsnerf_dense_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
+                       int n_views, const void* packed, size_t packed_bytes,
+                       const int32_t* act_pid, int64_t first, float* raw, void* workspace,
+                       void* stream);
+/* The two halves of mpsnerf_dense_bf16, same arguments: the cross-view transformer alone (tokens -> the two
+ * output tokens per point, bf16, in the workspace; lib/transformer.py:74-86) and the NeRF MLP alone
+ * (workspace -> raw; lib/skinnning_batch.py:449-473).  Calling one after the other equals the fused call. */
+int mpsnerf_xformer_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
+                       int n_views, const void* packed, size_t packed_bytes,
+                       const int32_t* act_pid, int64_t first, float* raw, void* workspace,
+                       void* stream);
+int mpsnerf_mlp_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
                        int n_views, const void* packed, size_t packed_bytes,
                        const int32_t* act_pid, int64_t first, float* raw, void* workspace,
                        void* stream);

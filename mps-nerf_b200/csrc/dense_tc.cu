@@ -1251,10 +1251,11 @@ extern "C" size_t mpsnerf_dense_bf16_workspace(int64_t count, int n_views) {
   return 2 * (c * mps::kTokLd * sizeof(__nv_bfloat16) + 256) + 256;
 }
 
-extern "C" int mpsnerf_dense_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
-                                  int n_views, const void* packed, size_t packed_bytes,
-                                  const int32_t* act_pid, int64_t first, float* raw, void* workspace,
-                                  void* stream) {
+// which: bit 0 = transformer (tokens -> tok0 / tok1 in the workspace), bit 1 = MLP (workspace -> raw)
+static int dense_bf16_impl(const void* tokens, int32_t ld, const float* xc, int64_t count,
+                           int n_views, const void* packed, size_t packed_bytes,
+                           const int32_t* act_pid, int64_t first, float* raw, void* workspace,
+                           void* stream, int which) {
   using namespace mps;
   MPS_REQUIRE(count >= 0 && n_views >= 2 && n_views <= 4);   // tensor-core path: 2..4 input views (fp32 path: up to 8)
   if (count == 0) return MPSNERF_OK;
@@ -1301,17 +1302,36 @@ extern "C" int mpsnerf_dense_bf16(const void* tokens, int32_t ld, const float* x
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, args);
   };
-#define MPS_T_CASE(V_, C_) if (n_views == V_ && cluster == C_) { \
+#define MPS_T_CASE(V_, C_) if ((which & 1) && n_views == V_ && cluster == C_) { \
     if (prof == 1) MPS_CUDA(launch(xformer_tc_kernel<V_, C_, true>, ta, kT_Smem, t_tiles, C_, kFThreads)); \
     else MPS_CUDA(launch(xformer_tc_kernel<V_, C_, false>, ta, kT_Smem, t_tiles, C_, kFThreads)); }
   MPS_T_CASE(2, 1) MPS_T_CASE(2, 2) MPS_T_CASE(2, 4)
   MPS_T_CASE(3, 1) MPS_T_CASE(3, 2) MPS_T_CASE(3, 4)
   MPS_T_CASE(4, 1) MPS_T_CASE(4, 2) MPS_T_CASE(4, 4)
 #undef MPS_T_CASE
-  if (cluster == 1) MPS_CUDA(launch(mlp_tc_kernel<1>, ma, kM_Smem, m_tiles, 1, kMThreads));
-  if (cluster == 2) MPS_CUDA(launch(mlp_tc_kernel<2>, ma, kM_Smem, m_tiles, 2, kMThreads));
-  if (cluster == 4) MPS_CUDA(launch(mlp_tc_kernel<4>, ma, kM_Smem, m_tiles, 4, kMThreads));
+  if ((which & 2) && cluster == 1) MPS_CUDA(launch(mlp_tc_kernel<1>, ma, kM_Smem, m_tiles, 1, kMThreads));
+  if ((which & 2) && cluster == 2) MPS_CUDA(launch(mlp_tc_kernel<2>, ma, kM_Smem, m_tiles, 2, kMThreads));
+  if ((which & 2) && cluster == 4) MPS_CUDA(launch(mlp_tc_kernel<4>, ma, kM_Smem, m_tiles, 4, kMThreads));
   return MPSNERF_OK;
+}
+
+extern "C" int mpsnerf_dense_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
+                                  int n_views, const void* packed, size_t packed_bytes,
+                                  const int32_t* act_pid, int64_t first, float* raw, void* workspace,
+                                  void* stream) {
+  return dense_bf16_impl(tokens, ld, xc, count, n_views, packed, packed_bytes, act_pid, first, raw, workspace, stream, 3);
+}
+extern "C" int mpsnerf_xformer_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
+                                    int n_views, const void* packed, size_t packed_bytes,
+                                    const int32_t* act_pid, int64_t first, float* raw, void* workspace,
+                                    void* stream) {
+  return dense_bf16_impl(tokens, ld, xc, count, n_views, packed, packed_bytes, act_pid, first, raw, workspace, stream, 1);
+}
+extern "C" int mpsnerf_mlp_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
+                                int n_views, const void* packed, size_t packed_bytes,
+                                const int32_t* act_pid, int64_t first, float* raw, void* workspace,
+                                void* stream) {
+  return dense_bf16_impl(tokens, ld, xc, count, n_views, packed, packed_bytes, act_pid, first, raw, workspace, stream, 2);
 }
 
 // Debug: copy the event trace (512 entries, see g_trace).

@@ -270,11 +270,13 @@ class RenderEngine:
                                                   first, _lib.ptr(raw), _lib.ptr(ws), _stream()), "dense_fp32")
                 _lib.count_launches(2 + 30)
             else:
-              with self.span("dense"):
-                _lib.check(lib.mpsnerf_dense_bf16(_lib.ptr(tokens), ld, _lib.ptr(xc), cnt, V, _lib.ptr(packed),
-                                                  packed.numel(), _lib.ptr(act_pid), first, _lib.ptr(raw),
-                                                  _lib.ptr(ws), _stream()), "dense_bf16")
-                _lib.count_launches(2 + 2)
+              dense_args = (_lib.ptr(tokens), ld, _lib.ptr(xc), cnt, V, _lib.ptr(packed), packed.numel(), _lib.ptr(act_pid),
+                            first, _lib.ptr(raw), _lib.ptr(ws), _stream())
+              with self.span("dense_t"):        # cross-view transformer (tcgen05), tokens -> tok0 / tok1
+                _lib.check(lib.mpsnerf_xformer_bf16(*dense_args), "xformer_bf16")
+              with self.span("dense_m"):        # NeRF MLP (tcgen05), tok0 / tok1 / x_c -> raw
+                _lib.check(lib.mpsnerf_mlp_bf16(*dense_args), "mlp_bf16")
+              _lib.count_launches(2 + 2)
             if dbg is not None:
                 dbg["xc"].append(xc[:3 * cnt].reshape(-1, 3).clone())
                 dbg["idx3"].append(idx3[:cnt].clone())
