@@ -27,6 +27,10 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_ACTIVE_POINT = 3514880          # algorithmic minimum, transformer + MLP
 WORKLOAD = "thuman_512x512_fullframe_V3_S64"
+# --workload h36m = BASELINE.json configs[2]: H36M-shaped 1000x1000 full frame, the rays of ONE target view
+# split in contiguous blocks over the ranks (strong scaling, no data-path collective); not the bench line
+WORKLOADS = {"thuman": ("thuman", "canonical_transformer.txt", WORKLOAD, "512x512"),
+             "h36m": ("h36m", "h36m.txt", "h36m_1000x1000_fullframe_V3_S64", "1000x1000")}
 
 
 def peaks():
@@ -70,14 +74,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows)}
 
 
-def build_scene_and_net(precision, target_view):
+def build_scene_and_net(precision, target_view, workload="thuman"):
     from mpsnerf_b200 import synthetic
     from mpsnerf_b200.lib import skinnning_batch as SB
     from mpsnerf_b200.model_selection import return_model
     from mpsnerf_b200.parser_config import config_parser
     from mpsnerf_b200 import run_nerf_batch as R
-    scene = synthetic.make_scene("thuman", seed=0)
-    if target_view != scene.target:          # other ranks render other target views of the same scene
+    kind, cfg_file = WORKLOADS[workload][:2]
+    scene = synthetic.make_scene(kind, seed=0)
+    if target_view is not None and target_view != scene.target:          # other ranks render other target views of the same scene
         K, Rm, T = scene.cams[target_view % 24]
         ro, rd = synthetic.get_rays(scene.H, scene.W, K, Rm, T)
         ro, rd = ro.reshape(-1, 3).copy(), rd.reshape(-1, 3).copy()
@@ -86,7 +91,7 @@ def build_scene_and_net(precision, target_view):
         scene.near, scene.far = np.zeros(len(ro), np.float32), np.ones(len(ro), np.float32)
         scene.near[hit], scene.far[hit] = n, f
     SB.set_default_smpl_models(scene.smpl)
-    args = config_parser().parse_args(["--config", os.path.join(ROOT, "configs", "canonical_transformer.txt"),
+    args = config_parser().parse_args(["--config", os.path.join(ROOT, "configs", cfg_file),
                                        "--N_samples", "64", "--precision", precision])
     R.configure(args)
     torch.manual_seed(0)
@@ -105,13 +110,40 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("MPSNERF_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # keep stdout to the one JSON line: NCCL / c10d print their version banner there during start-up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local)
     _lib.check(_lib.load().mpsnerf_check_device(local), "check_device")
-    scene, net, args = build_scene_and_net(a.precision, 1 + rank)
+    strong = a.workload != "thuman"
+    scene, net, args = build_scene_and_net(a.precision, None if strong else 1 + rank, a.workload)
     handle = R.NetworkHandle(net).to(dev).eval()
     rays_h, near_h, far_h = synthetic.rays_tensor(scene, None)
+    n_total = rays_h.shape[2]
+    if strong:                               # this rank's contiguous block of the one frame
+        # Balance by measured work, not by ray count: one untimed profiling render of the whole frame
+        # gives the active samples per ray; a ray costs ~0.6 active-point equivalents on its own (K1 + K6).
+        from mpsnerf_b200.parallel import balanced_ray_block
+        if world > 1:
+            dd = lambda d: {k: (v.to(dev) if torch.is_tensor(v) else dd(v) if isinstance(v, dict) else v) for k, v in d.items()}
+            ex = R.render(rays=rays_h.to(dev), near=near_h.to(dev), far=far_h.to(dev), sp_input=dd(scene.sp_input),
+                          tp_input=dd(scene.tp_input), network_fn=handle, N_samples=64, perturb=False, use_viewdirs=True)[3]
+            weights = ex["pts_mask"][0, ..., 0].sum(-1).double().cpu() + 0.6
+            del ex
+            torch.cuda.empty_cache()
+        else:
+            weights = scene.mask_at_box
+        s0, s1 = balanced_ray_block(weights, rank, world)
+        rays_h, near_h, far_h = rays_h[:, :, s0:s1].contiguous(), near_h[:, s0:s1].contiguous(), far_h[:, s0:s1].contiguous()
     n_rays = rays_h.shape[2]
 
     def pin(d):
@@ -222,16 +254,19 @@ def run_ours(a):
             dist.destroy_process_group()
         return
     cpu = cpu_baseline(budget_s=20.0)
+    rays_per_step = n_total if strong else n_rays * world
     res = {
-        "metric": "rays/sec (render fwd)", "value": n_rays * a.steps * world / (total_ms * 1e-3), "unit": "rays/s",
+        "metric": "rays/sec (render fwd)", "value": rays_per_step * a.steps / (total_ms * 1e-3), "unit": "rays/s",
         "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n_rays, "samples_per_ray": 64, "input_views": 3,
-                   "image": "512x512", "network": "configs/canonical_transformer.txt (skinning_batch), seeded random weights",
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": WORKLOADS[a.workload][2], "rays_per_gpu_per_step": n_rays, "samples_per_ray": 64, "input_views": 3,
+                   "image": WORKLOADS[a.workload][3], "network": "configs/%s (skinning_batch), seeded random weights" % WORKLOADS[a.workload][1],
                    "extras": "full reference contract (raw, pts_mask, smpl_query_pts, smpl_src_pts)",
                    "includes": "per-frame prep + encoder trunk + K1..K6", "l2": "flushed between timed steps (512 MiB fill)",
-                   "parallelism": f"rays: one target view per GPU x{world}"},
-        "e2e": {"value": n_rays * a.steps * world / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                   "parallelism": (f"rays: {world} contiguous blocks of one target view, balanced by active samples per ray "
+                                   f"(one untimed profiling render)" if strong
+                                   else f"rays: one target view per GPU x{world}")},
+        "e2e": {"value": rays_per_step * a.steps / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
@@ -288,6 +323,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MPSNERF_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="thuman", choices=sorted(WORKLOADS))
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -17,6 +17,24 @@ def ray_block(n_rays, rank, world):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def balanced_ray_block(weights, rank, world):
+    """[start, stop) of rank's contiguous block such that the blocks carry (nearly) equal total ``weights``.
+
+    ``weights`` (n_rays,) is a per-ray work estimate known before rendering -- e.g. the box mask of the ray
+    generator (rays that miss the body's box cost almost nothing) -- SURVEY 8e: "balance by in-box / active
+    counts, not raw rays".  Falls back to equal counts when all weights are zero."""
+    w = torch.as_tensor(weights, dtype=torch.float64).reshape(-1).cpu()
+    n = w.numel()
+    total = float(w.sum())
+    if total <= 0.0 or world == 1:
+        return ray_block(n, rank, world)
+    c = torch.cumsum(w, 0)
+    cuts = [0] + [int(torch.searchsorted(c, torch.tensor(total * r / world, dtype=torch.float64)).item()) for r in range(1, world)] + [n]
+    for i in range(1, len(cuts)):            # monotone, in range
+        cuts[i] = min(max(cuts[i], cuts[i - 1]), n)
+    return cuts[rank], cuts[rank + 1]
+
+
 def render_sharded(render_fn, rays, near, far, **kw):
     """Render this rank's block of ``rays (B,2,N,3)`` with ``render_fn`` (= run_nerf_batch.render).
 

@@ -51,6 +51,21 @@ def test_ray_blocks_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_blocks_partition():
+    from mpsnerf_b200.parallel import balanced_ray_block
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 9, 1000):
+        for w in (1, 2, 4, 8):
+            for weights in (torch.zeros(n), torch.ones(n), (torch.rand(n, generator=g) < 0.3).float(),
+                            torch.cat([torch.zeros(n // 2), torch.ones(n - n // 2)])):
+                blocks = [balanced_ray_block(weights, r, w) for r in range(w)]
+                assert blocks[0][0] == 0 and blocks[-1][1] == n
+                assert all(blocks[i][1] == blocks[i + 1][0] and blocks[i][0] <= blocks[i][1] for i in range(w - 1))
+                if weights.sum() >= 8 * w:           # every block within one ray's weight of the fair share
+                    share = float(weights.sum()) / w
+                    assert all(abs(float(weights[s:e].sum()) - share) <= 1.0 + 1e-9 for s, e in blocks)
+
+
 def test_sharded_render_two_ranks_gloo():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
