@@ -13,6 +13,7 @@ All per-point arithmetic happens in libmpsnerf_b200.so; torch is used for memory
 and the cuDNN encoder trunk only.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -77,6 +78,9 @@ class RenderEngine:
         self._packed = None
         self._packed_key = None
         self._smpl_cache = {}
+        self._trunk = None
+        self._prep_graphs = {}
+        self._use_prep_graph = os.environ.get("MPSNERF_PREP_GRAPH", "1") != "0"
         self.debug = None            # set to a dict to capture per-stage tensors (tests)
         self.timers = None           # set to a dict to record CUDA-event pairs per stage (bench.py)
         self.last_active = 0
@@ -122,6 +126,41 @@ class RenderEngine:
             self._smpl_cache[key] = tab
         return tab
 
+    # ------------------------------------------------------------------ encoder trunk (boundary: cuDNN)
+    @torch.no_grad()
+    def _encode(self, img):
+        """SpatialEncoder.forward (lib/encoder.py:256-306) for the shipped trunk shape (num_layers = 2, no first
+        pool, feature_scale = 0.5, eval mode), with BatchNorm folded into the convolutions and cuDNN's fused
+        conv+bias+ReLU / conv+bias+add+ReLU kernels: ~9 launches instead of ~35.  Any other trunk configuration
+        falls back to the module itself.  The folded weights are cached per parameter version."""
+        enc = self.net.encoder_2d
+        m = enc.model
+        ok = (enc.num_layers == 2 and not enc.use_first_pool and enc.feature_scale == 0.5 and not m.training
+              and img.shape[-1] % 2 == 0 and img.shape[-2] % 2 == 0
+              and all(type(b).__name__ == "BasicBlock" and b.downsample is None for b in m.layer1))
+        if not ok:
+            return enc(img)
+        key = tuple(p._version for p in m.parameters()) + tuple(b._version for b in m.buffers())
+        if self._trunk is None or self._trunk[0] != key or self._trunk[1][0][0].device != img.device:
+            def fold(conv, bn):
+                scale = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+                w = (conv.weight.double() * scale[:, None, None, None]).float().contiguous(memory_format=torch.channels_last)
+                b = (bn.bias.double() - bn.running_mean.double() * scale).float().contiguous()
+                return w, b
+            layers = [fold(m.conv1, m.bn1)] + [f for blk in m.layer1 for f in (fold(blk.conv1, blk.bn1), fold(blk.conv2, blk.bn2))]
+            self._trunk = (key, layers)
+        L = self._trunk[1]
+        # channels_last end to end: cuDNN's TF32 kernels are NHWC, and the NHWC view the gather wants is then free
+        x = F.avg_pool2d(img.float(), 2).contiguous(memory_format=torch.channels_last)   # == area interpolation at scale 0.5 for even sizes
+        x = torch.cudnn_convolution_relu(x, L[0][0], L[0][1], (2, 2), (3, 3), (1, 1), 1)
+        lat0 = x
+        for i in range(len(m.layer1)):
+            w1, b1 = L[1 + 2 * i]
+            w2, b2 = L[2 + 2 * i]
+            y = torch.cudnn_convolution_relu(x, w1, b1, (1, 1), (1, 1), (1, 1), 1)
+            x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, (1, 1), (1, 1), (1, 1), 1)
+        return torch.cat([lat0, x], dim=1)
+
     def _weights_fp32(self):
         sd = dict(self.net.named_parameters())
         tensors = [sd[k].detach() for k in DENSE_FP32_ORDER]
@@ -138,48 +177,88 @@ class RenderEngine:
             return self._prepare_frame(sp, tp, smpl)
 
     def _prepare_frame(self, sp, tp, smpl):
+        """~45 small launches (trunk, layout changes, K0, two grid builds) whose GPU time is ~0.45 ms but whose
+        launch overhead is ~1 ms when issued one by one behind an idle GPU: the sequence is captured once per
+        (shape, device, weights) into a CUDA graph over static input / output buffers and replayed per frame.
+        A FrameContext therefore stays valid until the next prepare_frame of this engine (the network keeps a
+        single-entry frame cache, lib/skinnning_batch.py::frame_context).  MPSNERF_PREP_GRAPH=0 disables it."""
         dev = sp["img_all"].device
-        lib = self.lib
         V = sp["img_all"].shape[0]
         assert 2 <= V <= _lib.MAX_VIEWS
-        H, W = sp["img_all"].shape[-2:]
+        f32 = lambda t: t.reshape(-1).float().contiguous()
+        ins = [sp["img_all"].float().contiguous()] + \
+              [f32(tp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
+              [f32(sp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
+              [f32(sp["R_all"]), f32(sp["T_all"]), f32(sp["K_all"]),
+               tp["vertices"].float().contiguous(), sp["t_vertices"].float().contiguous()]
+        if not self._use_prep_graph:
+            return self._prep_body(ins, smpl)
+        m = self.net.encoder_2d.model
+        key = (str(dev), self.precision, id(smpl), tuple(tuple(t.shape) for t in ins),
+               tuple(p._version for p in m.parameters()) + tuple(bf._version for bf in m.buffers()))
+        g = self._prep_graphs.get(key)
+        if g is None:
+            try:
+                static = [torch.empty_like(t) for t in ins]
+                torch._foreach_copy_(static, ins)
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):          # warm-up outside the capture (cuDNN plans, lazy inits)
+                    self._prep_body(static, smpl)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ctx = self._prep_body(static, smpl)
+                if len(self._prep_graphs) >= 4:
+                    self._prep_graphs.clear()
+                g = self._prep_graphs[key] = (graph, static, ctx)
+            except Exception:                          # capture not possible here: stay on the eager path
+                self._use_prep_graph = False
+                torch.cuda.synchronize(dev)
+                return self._prep_body(ins, smpl)
+        graph, static, ctx = g
+        torch._foreach_copy_(static, ins)
+        graph.replay()
+        _lib.count_launches(3)
+        return ctx
+
+    def _prep_body(self, ins, smpl):
+        img_all, keep, verts, tverts = ins[0], ins[1:12], ins[12], ins[13]
+        dev = img_all.device
+        lib = self.lib
+        V = img_all.shape[0]
+        H, W = img_all.shape[-2:]
         ctx = FrameContext()
         ctx.n_views = V
         # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
         # (cuDNN convolutions default to TF32; the fp32 precision mode keeps true fp32 end to end)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=(self.precision != "fp32")):
-            latent = self.net.encoder_2d(sp["img_all"])
+            latent = self._encode(img_all)
         ctx.latent = latent.permute(0, 2, 3, 1).contiguous().float()
-        ctx.img4 = F.pad(sp["img_all"].permute(0, 2, 3, 1), (0, 1)).contiguous().float()
+        ctx.img4 = F.pad(img_all.permute(0, 2, 3, 1), (0, 1)).contiguous().float()
         # K0: LBS transforms (target / big / source pose), cameras -> mpsnerf_frame, all on the device
         tab = self._smpl_tables(smpl, dev)
         ctx.skin_w = tab["weights"]
         ctx.frame_dev = torch.empty(ctypes.sizeof(_lib.Frame), dtype=torch.uint8, device=dev)
-        f32 = lambda t: t.reshape(-1).float().contiguous()
-        keep = [f32(tp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
-               [f32(sp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
-               [f32(sp["R_all"]), f32(sp["T_all"]), f32(sp["K_all"])]
         _lib.check(lib.mpsnerf_frame_prepare(*[_lib.ptr(t) for t in keep], V, W, H, latent.shape[-1], latent.shape[-2],
                                              _lib.ptr(tab["v_template"]), _lib.ptr(tab["shapedirs"]),
                                              _lib.ptr(tab["J_regressor"]), _lib.ptr(tab["parents"]),
                                              tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
                    "frame_prepare")
-        _lib.count_launches(1)
-        ctx.keep = keep
+        ctx.keep = list(ins)
 
-        nv = tp["vertices"].shape[0]
+        nv = verts.shape[0]
         gb = lib.mpsnerf_grid_bytes(nv)
         ctx.grid_tp = torch.empty(gb, dtype=torch.uint8, device=dev)
         ctx.grid_tv = torch.empty(gb, dtype=torch.uint8, device=dev)
-        verts = tp["vertices"].float().contiguous()
-        tverts = sp["t_vertices"].float().contiguous()
         fptr = ctx.frame_dev.data_ptr()
         _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, ctypes.c_void_p(fptr + _lib.Frame.Th_tp.offset),
                                           ctypes.c_void_p(fptr + _lib.Frame.R_tp.offset), GRID_CELL_TARGET,
                                           _lib.ptr(ctx.grid_tp), gb, _stream()), "grid_build(target)")
         _lib.check(lib.mpsnerf_grid_build(_lib.ptr(tverts), tverts.shape[0], None, None, GRID_CELL_TEMPLATE,
                                           _lib.ptr(ctx.grid_tv), gb, _stream()), "grid_build(template)")
-        _lib.count_launches(2)
+        if not torch.cuda.is_current_stream_capturing():
+            _lib.count_launches(3)
         return ctx
 
     # ------------------------------------------------------------------ the hot path
