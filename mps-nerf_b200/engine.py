@@ -79,6 +79,7 @@ class RenderEngine:
         self._packed_key = None
         self._smpl_cache = {}
         self._trunk = None
+        self._side = {}
         self._prep_graphs = {}
         self._use_prep_graph = os.environ.get("MPSNERF_PREP_GRAPH", "1") != "0"
         self.debug = None            # set to a dict to capture per-stage tensors (tests)
@@ -230,33 +231,47 @@ class RenderEngine:
         H, W = img_all.shape[-2:]
         ctx = FrameContext()
         ctx.n_views = V
-        # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
-        # (cuDNN convolutions default to TF32; the fp32 precision mode keeps true fp32 end to end)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=(self.precision != "fp32")):
-            latent = self._encode(img_all)
-        ctx.latent = latent.permute(0, 2, 3, 1).contiguous().float()
-        ctx.img4 = F.pad(img_all.permute(0, 2, 3, 1), (0, 1)).contiguous().float()
-        # K0: LBS transforms (target / big / source pose), cameras -> mpsnerf_frame, all on the device
+        # Three independent branches (graph edges when captured): the encoder trunk on the current stream,
+        # K0 -> target-pose grid on one side stream, the template grid on another.  K0 and the grid builds
+        # are single-CTA kernels (~0.1 ms each) that would otherwise queue up behind the trunk.
+        main = torch.cuda.current_stream()
+        sides = self._side.get(dev)
+        if sides is None:
+            sides = self._side[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         tab = self._smpl_tables(smpl, dev)
         ctx.skin_w = tab["weights"]
         ctx.frame_dev = torch.empty(ctypes.sizeof(_lib.Frame), dtype=torch.uint8, device=dev)
-        _lib.check(lib.mpsnerf_frame_prepare(*[_lib.ptr(t) for t in keep], V, W, H, latent.shape[-1], latent.shape[-2],
-                                             _lib.ptr(tab["v_template"]), _lib.ptr(tab["shapedirs"]),
-                                             _lib.ptr(tab["J_regressor"]), _lib.ptr(tab["parents"]),
-                                             tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
-                   "frame_prepare")
-        ctx.keep = list(ins)
-
         nv = verts.shape[0]
         gb = lib.mpsnerf_grid_bytes(nv)
         ctx.grid_tp = torch.empty(gb, dtype=torch.uint8, device=dev)
         ctx.grid_tv = torch.empty(gb, dtype=torch.uint8, device=dev)
-        fptr = ctx.frame_dev.data_ptr()
-        _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, ctypes.c_void_p(fptr + _lib.Frame.Th_tp.offset),
-                                          ctypes.c_void_p(fptr + _lib.Frame.R_tp.offset), GRID_CELL_TARGET,
-                                          _lib.ptr(ctx.grid_tp), gb, _stream()), "grid_build(target)")
-        _lib.check(lib.mpsnerf_grid_build(_lib.ptr(tverts), tverts.shape[0], None, None, GRID_CELL_TEMPLATE,
-                                          _lib.ptr(ctx.grid_tv), gb, _stream()), "grid_build(template)")
+        ctx.keep = list(ins)
+        Hf, Wf = ((H // 2 - 1) // 2 + 1, (W // 2 - 1) // 2 + 1)     # trunk output size: floor(H/2), then conv1 7x7 / 2 pad 3
+        for st in sides:
+            st.wait_stream(main)
+        with torch.cuda.stream(sides[0]):
+            # K0: LBS transforms (target / big / source pose), cameras -> mpsnerf_frame, all on the device
+            _lib.check(lib.mpsnerf_frame_prepare(*[_lib.ptr(t) for t in keep], V, W, H, Wf, Hf,
+                                                 _lib.ptr(tab["v_template"]), _lib.ptr(tab["shapedirs"]),
+                                                 _lib.ptr(tab["J_regressor"]), _lib.ptr(tab["parents"]),
+                                                 tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
+                       "frame_prepare")
+            fptr = ctx.frame_dev.data_ptr()
+            _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, ctypes.c_void_p(fptr + _lib.Frame.Th_tp.offset),
+                                              ctypes.c_void_p(fptr + _lib.Frame.R_tp.offset), GRID_CELL_TARGET,
+                                              _lib.ptr(ctx.grid_tp), gb, _stream()), "grid_build(target)")
+        with torch.cuda.stream(sides[1]):
+            _lib.check(lib.mpsnerf_grid_build(_lib.ptr(tverts), tverts.shape[0], None, None, GRID_CELL_TEMPLATE,
+                                              _lib.ptr(ctx.grid_tv), gb, _stream()), "grid_build(template)")
+        # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
+        # (cuDNN convolutions default to TF32; the fp32 precision mode keeps true fp32 end to end)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=(self.precision != "fp32")):
+            latent = self._encode(img_all)
+        assert latent.shape[-2:] == (Hf, Wf), (latent.shape, Hf, Wf)
+        ctx.latent = latent.permute(0, 2, 3, 1).contiguous().float()
+        ctx.img4 = F.pad(img_all.permute(0, 2, 3, 1), (0, 1)).contiguous().float()
+        for st in sides:
+            main.wait_stream(st)
         if not torch.cuda.is_current_stream_capturing():
             _lib.count_launches(3)
         return ctx
