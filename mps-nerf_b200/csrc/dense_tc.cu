@@ -2,19 +2,21 @@
 // and the canonical NeRF MLP ("M").  Restates lib/transformer.py:13-86 and
 // lib/skinnning_batch.py:438-473 with bf16 operands and fp32 accumulation.
 //
-// Structure (one persistent CTA per SM, 320 threads):
-//   warps 0-7  epilogue, 256 threads: thread (r = tid & 127, half = tid >> 7) owns half of the
-//              columns of row r (TMEM lane r; warps w and w+4 share lane quarter w & 3).  They turn
-//              accumulators into the next A operand (bias / ReLU / GELU / LayerNorm / attention)
+// Structure (one persistent CTA per SM, 640 threads = 5 warpgroups, setmaxnreg 104 / 40):
+//   warps 0-15 epilogue, 512 threads: thread (r = tid & 127, q = tid >> 7) owns a quarter of the
+//              columns of row r (TMEM lane r; warps w, w+4, w+8, w+12 share lane quarter w & 3).  They
+//              turn accumulators into the next A operand (bias / ReLU / GELU / LayerNorm / attention)
 //              and store it, bf16-packed, back into TENSOR MEMORY (tcgen05.st);
-//   warp 8     weight producer: one thread streams the pre-swizzled weight chunks with bulk
-//              async copies (TMA engine) into an mbarrier ring, in consumption order
-//              (multicast across the kC CTAs of a cluster);
-//   warp 9     MMA issuer: one thread issues TS-form tcgen05.mma (A from TMEM, B from smem, M = 128).
+//   warp 16    weight producer: streams the pre-swizzled weight chunks with bulk async copies (TMA
+//              engine) into an mbarrier ring, in consumption order (multicast across the kC CTAs of
+//              a cluster);
+//   warp 17    MMA issuer: TS-form tcgen05.mma (A from TMEM, B from smem, M = 128).  Both run fully
+//              converged with one elected lane issuing, so that operands stay in uniform registers.
 // Activations never leave the SM between layers and never touch shared memory: shared memory
-// holds only the weight ring (6-7 chunks in flight), which is what hides the L2 latency.
-// MMA <-> epilogue hand-over is a pair of mbarriers (a_bar: "A operand ready", 256 arrivals;
-// d_bar: "accumulator ready", tcgen05.commit).
+// holds only the weight ring, which is what hides the L2 latency.  MMA <-> epilogue hand-over is
+// by mbarriers (a_bar: "A operand ready", 512 arrivals; d_bar: "accumulator ready", tcgen05.commit).
+// Measured building blocks and the design rules derived from them: DESIGN.md section 5.1,
+// tools/ubench_tc.cu.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -25,9 +27,6 @@
 namespace mps {
 using namespace umma;
 
-constexpr int kTcThreads = 320;
-constexpr int kEpiThreads = 256;
-constexpr int kProdWarp = 8, kMmaWarp = 9;
 
 // ---- blob layout (must match mps-nerf_b200/pack.py)
 constexpr uint32_t kQkvChunk = 192 * 128, kWoChunk = 160 * 128, kW1Chunk = 128 * 128, kW2Chunk = 160 * 128;
@@ -71,26 +70,6 @@ struct Pipe {            // barriers of one CTA (in dynamic smem)
   uint32_t pad;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  // 0.5 x (1 + erf(x / sqrt 2)) with erf(z) = z * P(z^2) on |z| <= 3 (degree-9 Chebyshev fit, max
-  // |err| 1.6e-5 in fp32; saturates to +-0.99998 beyond).  Deliberately free of MUFU ops (ex2 / rcp):
-  // the special-function unit was the bottleneck of this epilogue (2 MUFU per element).
-  const float z = fminf(fmaxf(x * 0.70710678118654752440f, -3.0f), 3.0f);
-  const float w = z * z;
-  float p = -4.6617889859e-09f;
-  p = fmaf(p, w, 2.3821795289e-07f);
-  p = fmaf(p, w, -5.4625094310e-06f);
-  p = fmaf(p, w, 7.5274732228e-05f);
-  p = fmaf(p, w, -7.0841461755e-04f);
-  p = fmaf(p, w, 4.9218977801e-03f);
-  p = fmaf(p, w, -2.6500707362e-02f);
-  p = fmaf(p, w, 1.1261424783e-01f);
-  p = fmaf(p, w, -3.7607604539e-01f);
-  p = fmaf(p, w, 1.1283780006e+00f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, z * p, hx);
-}
-
 // GELU on two values at once in half precision: 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with the hardware
 // tanh.approx.f16x2 (one MUFU op per pair).  The three coefficients are a minimax fit of the erf form
 // (max |error| 2.5e-5 on the real line, 20x tighter than the usual two-term tanh form); the f16 arithmetic
@@ -115,60 +94,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// epilogue-side helpers shared by both kernels
-__device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpiThreads); }
-
-template <int kSlots, uint32_t kSlotBytes, int kC>
-struct Producer {            // used by the single producer thread
-  Pipe* pipe;
-  uint8_t* ring;
-  uint32_t crank;
-  uint32_t it = 0;
-  Prof pf;
-  long long acc_e = 0;
-  __device__ __forceinline__ void push(const uint8_t*& src, uint32_t bytes) {
-    const uint32_t slot = it % kSlots;
-    pf.start();
-    mbar_wait(&pipe->empty[slot], ((it / kSlots) & 1) ^ 1);
-    pf.stop(acc_e);
-    mbar_arrive_expect_tx(&pipe->full[slot], bytes);          // the whole chunk lands here (kC slices)
-    if (kC == 1) {
-      bulk_g2s(ring + slot * kSlotBytes, src, bytes, &pipe->full[slot]);
-    } else {
-      const uint32_t slice = bytes / kC;
-      bulk_g2s_mc(ring + slot * kSlotBytes + crank * slice, src + crank * slice, slice, &pipe->full[slot],
-                  (uint16_t)((1u << kC) - 1u));
-    }
-    src += bytes;
-    ++it;
-  }
-};
-
-template <int kSlots, uint32_t kSlotBytes, int kC>
-struct Consumer {            // used by the single MMA thread
-  Pipe* pipe;
-  uint32_t ring_addr;
-  uint32_t it = 0, g = 0;
-  Prof pf;
-  long long acc_a = 0, acc_w = 0;
-  __device__ __forceinline__ void wait_a() { pf.start(); mbar_wait(&pipe->a_bar[0], g & 1); pf.stop(acc_a); tc_fence_after(); }
-  __device__ __forceinline__ void done() { mma_commit(&pipe->d_bar[0]); ++g; }
-  __device__ __forceinline__ uint32_t slot_wait() {
-    const uint32_t slot = it % kSlots;
-    pf.start();
-    mbar_wait(&pipe->full[slot], (it / kSlots) & 1);
-    pf.stop(acc_w);
-    tc_fence_after();
-    return ring_addr + slot * kSlotBytes;
-  }
-  __device__ __forceinline__ void slot_free() {
-    if (kC == 1) mma_commit(&pipe->empty[it % kSlots]);
-    else mma_commit_mc(&pipe->empty[it % kSlots], (uint16_t)((1u << kC) - 1u));
-    ++it;
-  }
-};
-
-// Warp-converged versions (whole warp runs the control flow, one elected lane issues):
+// Weight ring: the whole warp runs the control flow, one elected lane issues.
 template <int kSlots, uint32_t kSlotBytes, int kC>
 struct RingProducer {
   Pipe* pipe;
