@@ -235,7 +235,9 @@ def run_ours(a):
     # HBM-side figures of the other kernels: algorithmic bytes / CUDA-event time
     n_pts, V = n_rays * 64, 3
     alg_bytes = {"k1_sample_knn": n_pts * 44 + n_rays * 32, "k3_deform": n_active * (20 + 48),
-                 "k4_gather": n_active * V * ((4 * 128 + 16) * 4 + 160 * (2 if a.precision == "bf16" else 4)),
+                 # K4: compulsory HBM bytes = tokens written + uv read + one pass over the latent / image planes;
+                 # its 4 taps x 128 channels per (point, view) are L2 hits (reported as l2_bytes below)
+                 "k4_gather": n_active * V * (8 + 160 * (2 if a.precision == "bf16" else 4)) + V * (128 * 128 * 128 + 512 * 512 * 4) * 4,
                  "k6_composite": n_rays * (64 * 16 + 52)}
     kernels = {k: {"bytes": b, "ms": stage_ms.get(k), "achieved_gbs": b / (stage_ms[k] * 1e-3) / 1e9,
                    "frac_of_hbm_peak": b / (stage_ms[k] * 1e-3) / 1e9 / pk["hbm"]} for k, b in alg_bytes.items() if stage_ms.get(k)}
@@ -245,6 +247,9 @@ def run_ours(a):
             t = n_active * fl / (stage_ms[k] * 1e-3) / 1e12
             kernels[k] = {"flop_per_active_point": fl, "ms": stage_ms[k], "achieved_tflops": t,
                           "frac_of_bf16_sustained_peak": t / pk["bf16_sustained"]}
+    if "k4_gather" in kernels:
+        kernels["k4_gather"]["l2_bytes"] = n_active * V * (4 * 128 + 16) * 4
+        kernels["k4_gather"]["l2_gbs"] = kernels["k4_gather"]["l2_bytes"] / (stage_ms["k4_gather"] * 1e-3) / 1e9
     roofline = {"bound": "tensor", "kernel": "dense_" + a.precision, "achieved": ach, "peak": pk["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["src"] + " sustained bf16",
                 "kernel_ms": dense_ms, "active_points": n_active, "flop_per_active_point": FLOP_PER_ACTIVE_POINT,
