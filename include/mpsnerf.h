@@ -180,6 +180,26 @@ int mpsnerf_mlp_bf16(const void* tokens, int32_t ld, const float* xc, int64_t co
                        const int32_t* act_pid, int64_t first, float* raw, void* workspace,
                        void* stream);
 
+/* ---- device-side active count ("_dc") variants of K3, K4 and K5 ------------------------
+ * Same work as the functions above for the active-list positions [first, first + n), where
+ * n = clamp(*count_dev - first, 0, capacity) is read ON THE DEVICE (count_dev = the counter K1 increments):
+ * the host can enqueue a whole frame without waiting for K1.  Buffers must hold `capacity` points; the
+ * debug outputs (idx3, xw) are not available.  The caller checks *count_dev <= first + capacity afterwards
+ * and runs the remainder, if any, through the host-count entry points. */
+int mpsnerf_deform_project_dc(const int32_t* act_pid, const int32_t* act_idx2, const float* act_q,
+                              int64_t first, int64_t capacity, const int32_t* count_dev, const float* skin_w,
+                              const mpsnerf_frame* frame, const void* grid_tv, float* xc, float* uv,
+                              float* smpl_src, void* stream);
+int mpsnerf_gather_tokens_f16_dc(const float* uv, int64_t first, int64_t capacity, const int32_t* count_dev,
+                                 int n_views, const mpsnerf_frame* frame, const float* latent,
+                                 const float* img4, void* tokens, void* stream);
+int mpsnerf_xformer_bf16_dc(const void* tokens, const float* xc, int64_t first, int64_t capacity,
+                            const int32_t* count_dev, int n_views, const void* packed, size_t packed_bytes,
+                            const int32_t* act_pid, float* raw, void* workspace, void* stream);
+int mpsnerf_mlp_bf16_dc(const void* tokens, const float* xc, int64_t first, int64_t capacity,
+                        const int32_t* count_dev, int n_views, const void* packed, size_t packed_bytes,
+                        const int32_t* act_pid, float* raw, void* workspace, void* stream);
+
 /* ---- K6: alpha compositing --------------------------------------------------------------
  * Replaces raw2outputs (run_nerf_batch.py:369-398).  One warp per ray.
  *   raw (n_rays,S,4); z is regenerated from rays/t_vals/u exactly as in K1, or read from

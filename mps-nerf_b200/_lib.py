@@ -44,6 +44,14 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mpsnerf_gather_tokens": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                       c_void_p]),
+    "mpsnerf_deform_project_dc": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_gather_tokens_f16_dc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p]),
+    "mpsnerf_xformer_bf16_dc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_mlp_bf16_dc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
     "mpsnerf_gen_rays": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_gather_tokens_f16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_dense_fp32_workspace": (c_size_t, [c_int64, c_int]),

@@ -68,7 +68,11 @@ deform_project_kernel(const int32_t* __restrict__ act_pid, const int32_t* __rest
                       const float* __restrict__ skin_w, const mpsnerf_frame* __restrict__ frame,
                       const char* __restrict__ grid_buf, float* __restrict__ xc_out, float* __restrict__ uv_out,
                       float* __restrict__ smpl_src, int32_t* __restrict__ idx3_out, float* __restrict__ xw_out,
-                      int identity_canonical) {
+                      int identity_canonical, const int32_t* __restrict__ count_dev) {
+  if (count_dev != nullptr) {          // device-side active count: `count` is only the capacity of the slab
+    const int64_t n = (int64_t)*count_dev - first;
+    count = n < count ? (n > 0 ? n : 0) : count;
+  }
   __shared__ mpsnerf_frame s_fr;
   __shared__ GridHdr s_hdr;
   const GridView g = grid_view(grid_buf);
@@ -155,11 +159,11 @@ deform_project_kernel(const int32_t* __restrict__ act_pid, const int32_t* __rest
 
 }  // namespace mps
 
-extern "C" int mpsnerf_deform_project(const int32_t* act_pid, const int32_t* act_idx2, const float* act_q,
-                                      int64_t first, int64_t count, const float* skin_w,
-                                      const mpsnerf_frame* frame, const void* grid_tv, float* xc, float* uv,
-                                      float* smpl_src, int32_t* idx3, float* xw, int identity_canonical,
-                                      void* stream) {
+static int deform_project_impl(const int32_t* act_pid, const int32_t* act_idx2, const float* act_q,
+                               int64_t first, int64_t count, const float* skin_w,
+                               const mpsnerf_frame* frame, const void* grid_tv, float* xc, float* uv,
+                               float* smpl_src, int32_t* idx3, float* xw, int identity_canonical,
+                               const int32_t* count_dev, void* stream) {
   MPS_REQUIRE(first >= 0 && count >= 0);
   if (count == 0) return MPSNERF_OK;
   MPS_REQUIRE(act_pid && act_q && skin_w && frame && grid_tv && xc && uv);
@@ -169,7 +173,24 @@ extern "C" int mpsnerf_deform_project(const int32_t* act_pid, const int32_t* act
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
   mps::deform_project_kernel<<<(int)blocks, mps::kK3Threads, 0, (cudaStream_t)stream>>>(
       act_pid, act_idx2, act_q, first, count, skin_w, frame, static_cast<const char*>(grid_tv), xc, uv,
-      smpl_src, idx3, xw, identity_canonical);
+      smpl_src, idx3, xw, identity_canonical, count_dev);
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
+}
+
+extern "C" int mpsnerf_deform_project(const int32_t* act_pid, const int32_t* act_idx2, const float* act_q,
+                                      int64_t first, int64_t count, const float* skin_w,
+                                      const mpsnerf_frame* frame, const void* grid_tv, float* xc, float* uv,
+                                      float* smpl_src, int32_t* idx3, float* xw, int identity_canonical,
+                                      void* stream) {
+  return deform_project_impl(act_pid, act_idx2, act_q, first, count, skin_w, frame, grid_tv, xc, uv, smpl_src, idx3, xw,
+                             identity_canonical, nullptr, stream);
+}
+extern "C" int mpsnerf_deform_project_dc(const int32_t* act_pid, const int32_t* act_idx2, const float* act_q,
+                                         int64_t first, int64_t capacity, const int32_t* count_dev, const float* skin_w,
+                                         const mpsnerf_frame* frame, const void* grid_tv, float* xc, float* uv,
+                                         float* smpl_src, void* stream) {
+  MPS_REQUIRE(count_dev != nullptr);
+  return deform_project_impl(act_pid, act_idx2, act_q, first, capacity, skin_w, frame, grid_tv, xc, uv, smpl_src, nullptr,
+                             nullptr, 0, count_dev, stream);
 }

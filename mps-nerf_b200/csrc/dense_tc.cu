@@ -202,6 +202,8 @@ struct TArgs {
   __nv_bfloat16* tok0;   // (count, 160)
   __nv_bfloat16* tok1;
   int prof;
+  const int32_t* count_dev;   // optional device-side active count (count is then the slab capacity)
+  int64_t first;
 };
 
 // LayerNorm over the 155 real columns of a row whose 160 columns are split between four threads
@@ -259,7 +261,12 @@ __device__ __forceinline__ void load_x40(uint32_t taddr, float (&x)[40]) {
 // each chunk crosses L2 -> SM once per cluster.  A ring slot is reused only after the MMA warps of
 // *all* kC CTAs have released it (empty barriers count kC arrivals, delivered by multicast commits).
 template <int kV, int kC, bool kProf>
-__global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a) {
+__global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_in) {
+  TArgs a = a_in;
+  if (a.count_dev != nullptr) {
+    const int64_t n = (int64_t)*a.count_dev - a.first;
+    a.count = n < a.count ? (n > 0 ? n : 0) : a.count;
+  }
   extern __shared__ __align__(1024) uint8_t smem[];
   Pipe* pipe = reinterpret_cast<Pipe*>(smem + kT_PIPE);
   float* FP = reinterpret_cast<float*>(smem + kT_FP);
@@ -628,6 +635,8 @@ struct MArgs {
   const int32_t* act_pid;   // already offset by `first`
   float* raw;               // (P, 4)
   int prof;
+  const int32_t* count_dev;   // optional device-side active count (count is then the slab capacity)
+  int64_t first;
 };
 
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
@@ -738,7 +747,12 @@ __device__ __forceinline__ void token_store(uint32_t taddr, int q, const uint32_
 }
 
 template <int kC>
-__global__ void __launch_bounds__(kMThreads, 1) mlp_tc_kernel(const MArgs a) {
+__global__ void __launch_bounds__(kMThreads, 1) mlp_tc_kernel(const MArgs a_in) {
+  MArgs a = a_in;
+  if (a.count_dev != nullptr) {
+    const int64_t n = (int64_t)*a.count_dev - a.first;
+    a.count = n < a.count ? (n > 0 ? n : 0) : a.count;
+  }
   extern __shared__ __align__(1024) uint8_t smem[];
   Pipe* pipe = reinterpret_cast<Pipe*>(smem + kM_PIPE);
   float* FP = reinterpret_cast<float*>(smem + kM_FP);
@@ -1181,7 +1195,7 @@ extern "C" size_t mpsnerf_dense_bf16_workspace(int64_t count, int n_views) {
 static int dense_bf16_impl(const void* tokens, int32_t ld, const float* xc, int64_t count,
                            int n_views, const void* packed, size_t packed_bytes,
                            const int32_t* act_pid, int64_t first, float* raw, void* workspace,
-                           void* stream, int which) {
+                           void* stream, int which, const int32_t* count_dev = nullptr) {
   using namespace mps;
   MPS_REQUIRE(count >= 0 && n_views >= 2 && n_views <= 4);   // tensor-core path: 2..4 input views (fp32 path: up to 8)
   if (count == 0) return MPSNERF_OK;
@@ -1204,8 +1218,8 @@ static int dense_bf16_impl(const void* tokens, int32_t ld, const float* xc, int6
   }
   static int prof = -1;
   if (prof < 0) { const char* e = getenv("MPSNERF_TC_PROF"); prof = e ? atoi(e) : 0; }
-  TArgs ta{static_cast<const __half*>(tokens), ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof};
-  MArgs ma{tok0, tok1, xc, count, static_cast<const uint8_t*>(packed), act_pid + first, raw, prof};
+  TArgs ta{static_cast<const __half*>(tokens), ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof, count_dev, first};
+  MArgs ma{tok0, tok1, xc, count, static_cast<const uint8_t*>(packed), act_pid + first, raw, prof, count_dev, first};
   const int ppt = 128 / n_views;
   const int64_t t_tiles = (count + ppt - 1) / ppt, m_tiles = (count + 127) / 128;
   auto launch = [&](auto kernel, const auto& args, size_t smem_bytes, int64_t tiles, int kc, int threads) -> cudaError_t {
@@ -1252,6 +1266,22 @@ extern "C" int mpsnerf_xformer_bf16(const void* tokens, int32_t ld, const float*
                                     const int32_t* act_pid, int64_t first, float* raw, void* workspace,
                                     void* stream) {
   return dense_bf16_impl(tokens, ld, xc, count, n_views, packed, packed_bytes, act_pid, first, raw, workspace, stream, 1);
+}
+// Device-side count variants: `capacity` points of buffer space starting at active-list position `first`; the number
+// actually processed is clamp(*count_dev - first, 0, capacity), read on the device -- no host round trip.
+extern "C" int mpsnerf_xformer_bf16_dc(const void* tokens, const float* xc, int64_t first, int64_t capacity,
+                                       const int32_t* count_dev, int n_views, const void* packed, size_t packed_bytes,
+                                       const int32_t* act_pid, float* raw, void* workspace, void* stream) {
+  MPS_REQUIRE(count_dev != nullptr);
+  return dense_bf16_impl(tokens, MPSNERF_TOKEN_LD, xc, capacity, n_views, packed, packed_bytes, act_pid, first, raw, workspace,
+                         stream, 1, count_dev);
+}
+extern "C" int mpsnerf_mlp_bf16_dc(const void* tokens, const float* xc, int64_t first, int64_t capacity,
+                                   const int32_t* count_dev, int n_views, const void* packed, size_t packed_bytes,
+                                   const int32_t* act_pid, float* raw, void* workspace, void* stream) {
+  MPS_REQUIRE(count_dev != nullptr);
+  return dense_bf16_impl(tokens, MPSNERF_TOKEN_LD, xc, capacity, n_views, packed, packed_bytes, act_pid, first, raw, workspace,
+                         stream, 2, count_dev);
 }
 extern "C" int mpsnerf_mlp_bf16(const void* tokens, int32_t ld, const float* xc, int64_t count,
                                 int n_views, const void* packed, size_t packed_bytes,

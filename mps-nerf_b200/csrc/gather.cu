@@ -59,7 +59,12 @@ __device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, const 
 template <bool kHalf>
 __global__ void __launch_bounds__(kK4Threads)
 gather_tokens_kernel(const float* __restrict__ uv, int64_t n_rows /* count*V */, int V, const mpsnerf_frame* __restrict__ frame,
-                     const float* __restrict__ latent, const float* __restrict__ img4, void* __restrict__ tokens_v, int ld) {
+                     const float* __restrict__ latent, const float* __restrict__ img4, void* __restrict__ tokens_v, int ld,
+                     const int32_t* __restrict__ count_dev, int64_t first) {
+  if (count_dev != nullptr) {          // device-side active count: n_rows is only the capacity of the slab
+    const int64_t n = ((int64_t)*count_dev - first) * V;
+    n_rows = n < n_rows ? (n > 0 ? n : 0) : n_rows;
+  }
   float* tokens = static_cast<float*>(tokens_v);
   __half* tokens_h = static_cast<__half*>(tokens_v);
   auto clamp_h = [](float x) { return fminf(fmaxf(x, -65504.f), 65504.f); };
@@ -135,13 +140,14 @@ extern "C" int mpsnerf_gather_tokens(const float* uv, int64_t count, int n_views
   int64_t blocks = (rows + mps::kK4Threads - 1) / mps::kK4Threads;      // a warp takes 32 rows per visit
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
   mps::gather_tokens_kernel<false><<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
-      uv, rows, n_views, frame, latent, img4, tokens, ld);
+      uv, rows, n_views, frame, latent, img4, tokens, ld, nullptr, 0);
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
 }
 
-extern "C" int mpsnerf_gather_tokens_f16(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
-                                         const float* latent, const float* img4, void* tokens, void* stream) {
+static int gather_tokens_f16_impl(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
+                                  const float* latent, const float* img4, void* tokens, const int32_t* count_dev,
+                                  int64_t first, void* stream) {
   MPS_REQUIRE(count >= 0 && n_views >= 1 && n_views <= MPSNERF_MAX_VIEWS);
   if (count == 0) return MPSNERF_OK;
   MPS_REQUIRE(uv && frame && latent && img4 && tokens);
@@ -151,7 +157,18 @@ extern "C" int mpsnerf_gather_tokens_f16(const float* uv, int64_t count, int n_v
   int64_t blocks = (rows + mps::kK4Threads - 1) / mps::kK4Threads;
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
   mps::gather_tokens_kernel<true><<<(int)blocks, mps::kK4Threads, 0, (cudaStream_t)stream>>>(
-      uv, rows, n_views, frame, latent, img4, tokens, MPSNERF_TOKEN_LD);
+      uv, rows, n_views, frame, latent, img4, tokens, MPSNERF_TOKEN_LD, count_dev, first);
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
+}
+
+extern "C" int mpsnerf_gather_tokens_f16(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
+                                         const float* latent, const float* img4, void* tokens, void* stream) {
+  return gather_tokens_f16_impl(uv, count, n_views, frame, latent, img4, tokens, nullptr, 0, stream);
+}
+extern "C" int mpsnerf_gather_tokens_f16_dc(const float* uv, int64_t first, int64_t capacity, const int32_t* count_dev,
+                                            int n_views, const mpsnerf_frame* frame, const float* latent,
+                                            const float* img4, void* tokens, void* stream) {
+  MPS_REQUIRE(count_dev != nullptr && first >= 0);
+  return gather_tokens_f16_impl(uv, capacity, n_views, frame, latent, img4, tokens, count_dev, first, stream);
 }

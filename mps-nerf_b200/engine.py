@@ -72,13 +72,15 @@ class RenderEngine:
         assert precision in ("fp32", "bf16")
         self.net = net
         self.precision = precision
-        self.slab = slab or (32768 if precision == "fp32" else 1 << 20)
+        self.slab = slab or (32768 if precision == "fp32" else 1 << 21)
         self.lib = _lib.load()
         self._ws = {}
         self._packed = None
         self._packed_key = None
         self._smpl_cache = {}
         self._trunk = None
+        self._pinned = {}
+        self._use_device_count = os.environ.get("MPSNERF_DEVICE_COUNT", "1") != "0"
         self._side = {}
         self._prep_graphs = {}
         self._use_prep_graph = os.environ.get("MPSNERF_PREP_GRAPH", "1") != "0"
@@ -304,6 +306,7 @@ class RenderEngine:
         act_idx2 = self._buf("act_idx2", 4 * P, dev).view(torch.int32)
         act_q = self._buf("act_q", 12 * P, dev).view(torch.float32)
         counter = self._buf("counter", 256, dev).view(torch.int32)
+        device_count = False
         if all_active:      # extract_mesh: every point is evaluated, canonical = the point itself
             act_pid[:P] = torch.arange(P, device=dev, dtype=torch.int32)
             act_q[:3 * P] = points.reshape(-1)
@@ -319,7 +322,27 @@ class RenderEngine:
                 _lib.ptr(ctx.grid_tp), _lib.ptr(raw), _lib.ptr(mask), _lib.ptr(sq), _lib.ptr(ss), _lib.ptr(act_pid),
                 _lib.ptr(act_idx2), _lib.ptr(act_q), _lib.ptr(counter), _stream()), "sample_knn")
             _lib.count_launches(1)
-            n_act = int(counter[0].item())          # the one host sync of the frame
+            # Device-side count (tensor-core path): K3, K4, T and M are enqueued right behind K1 for the first
+            # `cap` active points and read the real count on the device; the host reads it from pinned memory
+            # only after everything is in the queue, so the GPU never waits for the CPU in the middle of a
+            # frame.  Whatever exceeds `cap` goes through the host-count path below.
+            device_count = (self.precision == "bf16" and self.debug is None and self._use_device_count)
+            if device_count:
+                cap = int(min(self.slab, P))
+                pinned = self._pinned_count(dev)
+                pinned.copy_(counter[:1], non_blocking=True)
+                count_event = torch.cuda.Event()
+                count_event.record()
+                self._dense_slab_dc(ctx, V, cap, counter, act_pid, act_idx2, act_q, ss, raw, dev)
+                done_upto = cap
+            else:
+                n_act = int(counter[0].item())          # host-count path: the one host sync of the frame
+                done_upto = 0
+        if not all_active and device_count:
+            count_event.synchronize()
+            n_act = int(pinned[0])
+        elif all_active:
+            done_upto = 0
         out["n_active"] = n_act
         self.last_active = n_act
         dbg = self.debug
@@ -328,8 +351,8 @@ class RenderEngine:
                        act_q=act_q[:3 * n_act].reshape(-1, 3).clone(), xc=[], idx3=[], xw=[], uv=[], tokens=[])
         ld = _lib.TOKEN_DIM if self.precision == "fp32" else _lib.TOKEN_LD
         slab = self.slab
-        if n_act:
-            cap = min(slab, n_act)
+        if n_act > done_upto:
+            cap = min(slab, n_act - done_upto)
             xc = self._buf("xc", 12 * cap, dev).view(torch.float32)
             uv = self._buf("uv", 8 * V * cap, dev).view(torch.float32)
             if self.precision == "fp32":
@@ -344,7 +367,7 @@ class RenderEngine:
                 ws = self._buf("dense", lib.mpsnerf_dense_bf16_workspace(cap, V), dev)
             idx3 = self._buf("idx3", 4 * cap, dev).view(torch.int32) if dbg is not None else None
             xw = self._buf("xw", 12 * cap, dev).view(torch.float32) if dbg is not None else None
-        for first in range(0, n_act, slab):
+        for first in range(done_upto, n_act, slab):
             cnt = min(slab, n_act - first)
             with self.span("k3_deform"):
               _lib.check(lib.mpsnerf_deform_project(
@@ -389,6 +412,37 @@ class RenderEngine:
             _lib.count_launches(1)
             out.update(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth)
         return out
+
+    def _pinned_count(self, dev):
+        t = self._pinned.get(dev)
+        if t is None:
+            t = self._pinned[dev] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        return t
+
+    def _dense_slab_dc(self, ctx, V, cap, counter, act_pid, act_idx2, act_q, ss, raw, dev):
+        """K3, K4, T, M for the active-list positions [0, min(count, cap)), count read on the device."""
+        lib = self.lib
+        ld = _lib.TOKEN_LD
+        xc = self._buf("xc", 12 * cap, dev).view(torch.float32)
+        uv = self._buf("uv", 8 * V * cap, dev).view(torch.float32)
+        tokens = self._buf("tokens", 2 * ld * V * cap, dev).view(torch.float16)
+        packed = self._packed_weights(dev)
+        ws = self._buf("dense", lib.mpsnerf_dense_bf16_workspace(cap, V), dev)
+        with self.span("k3_deform"):
+            _lib.check(lib.mpsnerf_deform_project_dc(_lib.ptr(act_pid), _lib.ptr(act_idx2), _lib.ptr(act_q), 0, cap, _lib.ptr(counter),
+                                                     _lib.ptr(ctx.skin_w), _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.grid_tv),
+                                                     _lib.ptr(xc), _lib.ptr(uv), _lib.ptr(ss), _stream()), "deform_project_dc")
+        with self.span("k4_gather"):
+            _lib.check(lib.mpsnerf_gather_tokens_f16_dc(_lib.ptr(uv), 0, cap, _lib.ptr(counter), V, _lib.ptr(ctx.frame_dev),
+                                                        _lib.ptr(ctx.latent), _lib.ptr(ctx.img4), _lib.ptr(tokens), _stream()),
+                       "gather_tokens_f16_dc")
+        dense_args = (_lib.ptr(tokens), _lib.ptr(xc), 0, cap, _lib.ptr(counter), V, _lib.ptr(packed), packed.numel(),
+                      _lib.ptr(act_pid), _lib.ptr(raw), _lib.ptr(ws), _stream())
+        with self.span("dense_t"):
+            _lib.check(lib.mpsnerf_xformer_bf16_dc(*dense_args), "xformer_bf16_dc")
+        with self.span("dense_m"):
+            _lib.check(lib.mpsnerf_mlp_bf16_dc(*dense_args), "mlp_bf16_dc")
+        _lib.count_launches(4)
 
     def _packed_weights(self, dev):
         from .pack import pack_weights_bf16

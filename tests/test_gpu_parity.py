@@ -365,3 +365,64 @@ def test_raygen_against_reference_golden_and_oracle():
     np.testing.assert_allclose(r8.cpu().numpy(), o8, rtol=3e-7, atol=1e-7)
     ro, rd = U.get_rays(scene.H, scene.W, K, R, T)
     assert ro.shape == (scene.H, scene.W, 3) and torch.equal(rd.reshape(-1, 3), r8[:, 3:6])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_prep_graph_replay_matches_eager(precision, monkeypatch):
+    """The CUDA-graph replay of the per-frame preparation (engine._prepare_frame) must track its inputs: two
+    different frames of the same shape, alternated, give exactly what a graph-free engine gives."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    scenes = [synthetic.make_scene("thuman", seed=s, H=128, W=128, novel_pose=bool(s)) for s in (0, 1)]
+    sd = synthetic.seeded_state_dict(0, 300.0)
+
+    def renders(order, graph):
+        monkeypatch.setenv("MPSNERF_PREP_GRAPH", "1" if graph else "0")
+        net = R.NetworkHandle(make_net(scenes[0], sd, precision))
+        eng = net.module.engine() if hasattr(net, "module") else None
+        outs = []
+        for i in order:
+            sc = scenes[i]
+            ids = synthetic.inbox_ray_subset(sc, 200)
+            rays, near, far = synthetic.rays_tensor(sc, ids, device="cuda")
+            rgb, disp, acc, ex = R.render(rays=rays, near=near, far=far, sp_input=_cuda_dict(sc.sp_input), tp_input=_cuda_dict(sc.tp_input),
+                                          network_fn=net, N_samples=32, perturb=False, use_viewdirs=True)
+            outs.append((rgb.clone(), ex["raw"].clone(), ex["pts_mask"].clone(), ex["smpl_src_pts"].clone()))
+        return outs, eng
+
+    order = [0, 1, 0, 1, 1, 0]
+    got, eng = renders(order, True)
+    if eng is not None:
+        assert eng._use_prep_graph and len(eng._prep_graphs) == 1      # captured once, replayed for both frames
+    want, _ = renders(order, False)
+    for a, b in zip(got, want):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert not torch.equal(got[0][1], got[1][1])                          # the two frames really differ
+
+
+@pytest.mark.gpu
+def test_device_count_overflow_and_host_count_agree(monkeypatch):
+    """bf16 path: (a) device-side active count with ample capacity, (b) capacity smaller than the active count
+    (the remainder goes through the host-count entry points), (c) host-count only -- all bit-identical."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    scene, sd, g = load_case("plain")
+    ids = synthetic.inbox_ray_subset(scene, 300)
+    rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+
+    def run(slab, device_count):
+        monkeypatch.setenv("MPSNERF_DEVICE_COUNT", "1" if device_count else "0")
+        net = R.NetworkHandle(make_net(scene, sd, "bf16"))
+        eng = net.module.engine()
+        if slab:
+            eng.slab = slab
+        rgb, disp, acc, ex = R.render(rays=rays, near=near, far=far, sp_input=sp, tp_input=tp, network_fn=net, N_samples=64,
+                                      perturb=False, use_viewdirs=True)
+        torch.cuda.synchronize()
+        return rgb, ex["raw"], ex["smpl_src_pts"], eng.last_active
+
+    a, b, c = run(None, True), run(500, True), run(None, False)
+    assert a[3] == b[3] == c[3] and a[3] > 2 * 500       # the small capacity really overflows (two extra slabs)
+    for x, y, z in zip(a[:3], b[:3], c[:3]):
+        assert torch.equal(x, y) and torch.equal(x, z)
