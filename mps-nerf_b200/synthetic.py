@@ -164,6 +164,9 @@ def make_scene(kind="thuman", seed=0, gender="n", H=None, W=None, n_views=3, nov
     W = W or base_hw
     focal = focal * W / base_hw
     inputs, target = ([4, 12, 20], 1) if kind == "thuman" else ([0, 1, 2], 3)
+    if n_views > len(inputs):          # more input views than the dataset default: take further ring cameras
+        assert kind == "thuman" and n_views <= 8
+        inputs = inputs + [c for c in (8, 16, 0, 22, 10) if c != target][:n_views - len(inputs)]
     inputs = inputs[:n_views]
 
     def params(r):

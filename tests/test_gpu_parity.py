@@ -426,3 +426,28 @@ def test_device_count_overflow_and_host_count_agree(monkeypatch):
     assert a[3] == b[3] == c[3] and a[3] > 2 * 500       # the small capacity really overflows (two extra slabs)
     for x, y, z in zip(a[:3], b[:3], c[:3]):
         assert torch.equal(x, y) and torch.equal(x, z)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_views", [2, 4])
+def test_other_view_counts_against_oracle(n_views):
+    """view_num != 3: the fused kernels are specialised per view count (tile = 128 // V points); both
+    precisions against the oracle on a small synthetic scene."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    from oracle import oracle as O
+    scene = synthetic.make_scene("thuman", seed=3, H=128, W=128, n_views=n_views)
+    sd = synthetic.seeded_state_dict(3, 100.0)
+    ids = synthetic.inbox_ray_subset(scene, 160)
+    ref = O.render(O.smpl_tensors(scene.smpl), sd, scene.sp_input, scene.tp_input, scene.rays_o[ids], scene.rays_d[ids],
+                   scene.near[ids], scene.far[ids], S=48)
+    rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
+    for precision, tol in (("fp32", 2e-4), ("bf16", 1e-2)):
+        net = R.NetworkHandle(make_net(scene, sd, precision))
+        rgb, disp, acc, ex = R.render(rays=rays, near=near, far=far, sp_input=_cuda_dict(scene.sp_input),
+                                      tp_input=_cuda_dict(scene.tp_input), network_fn=net, N_samples=48, perturb=False,
+                                      use_viewdirs=True)
+        mask = ex["pts_mask"][0, ..., 0].cpu().numpy() > 0.5
+        assert ex["raw"].shape[1] == 160 and scene.sp_input["img_all"].shape[1] == n_views
+        assert (mask != (ref["pts_mask"][..., 0] > 0.5)).sum() <= 1 and mask.sum() > 200
+        assert float(np.abs(rgb[0].cpu().numpy() - ref["rgb_map"]).max()) <= tol
+        assert float(np.abs(acc[0].cpu().numpy() - ref["acc_map"]).max()) <= tol
