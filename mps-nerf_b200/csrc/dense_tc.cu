@@ -66,6 +66,8 @@ struct Pipe {            // barriers of one CTA (in dynamic smem)
   uint64_t d_bar[2];    // "accumulator ready" (M kernel: one per N-half)
   uint64_t k_bar;       // M kernel: "[h1: K0] done, HT K-half 0 may be overwritten"
   uint64_t r_bar;       // T kernel: "scratch accumulator R has been copied out" (early release)
+  uint64_t q_bar[2];    // T kernel: "q|k|v of this team's next head is in R" (tcgen05.commit)
+  uint64_t o_bar[2];    // T kernel: "this team's attention output is in its half of OT" (256 arrivals)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -180,12 +182,14 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float* v) {
 //   OT [432,496)  attention output of one head (K = 64, 32 cols) or GELU(FF hidden) (K = 128, 64 cols)
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kT_ColX = 0, kT_ColR = 160, kT_ColY = 352, kT_ColO = 432;
-constexpr uint32_t kT_KX = 0;                      // k of the current head, fp32 [128][64], rows of 256 B, unit-swizzled
-constexpr uint32_t kT_VX = kT_KX + 32768;          // v of the current head, fp16 [128][64], rows of 128 B, unit-swizzled
-constexpr uint32_t kT_PD = kT_VX + 16384;          // partial q.k dots  float[4][128][4]
-constexpr uint32_t kT_LS = kT_PD + 8192;           // LayerNorm partial sums float[2][4][128]
-constexpr uint32_t kT_RING = kT_LS + 4096;         // 1024-aligned: 32768 + 16384 + 8192 + 4096 = 61440 = 60 * 1024
-constexpr int kT_Slots = 6;
+// attention exchange area, one set per team (the two teams work on different heads at the same time):
+constexpr uint32_t kT_KX = 0;                      // k of the team's head, fp16 [128][64], rows of 128 B, unit-swizzled
+constexpr uint32_t kT_VX = 16384;                  // v of the team's head, fp16, same layout
+constexpr uint32_t kT_PD = 32768;                  // partial q.k dots  float[2][128][4]
+constexpr uint32_t kT_TeamBytes = 36864;
+constexpr uint32_t kT_LS = 2 * kT_TeamBytes;       // LayerNorm partial sums float[2][4][128]
+constexpr uint32_t kT_RING = kT_LS + 4096;         // 1024-aligned: 2 * 36864 + 4096 = 77824 = 76 * 1024
+constexpr int kT_Slots = 5;
 constexpr uint32_t kT_SlotBytes = kQkvChunk;
 constexpr uint32_t kT_FP = kT_RING + kT_Slots * kT_SlotBytes;
 constexpr uint32_t kT_PIPE = kT_FP + ((kTFloats * 4 + 15) / 16) * 16;
@@ -281,7 +285,8 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     for (int i = 0; i < kT_Slots; ++i) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], kC); }
     mbar_init(&pipe->a_bar[0], kFEpiThreads);
     mbar_init(&pipe->d_bar[0], 1);
-    mbar_init(&pipe->r_bar, kFEpiThreads);
+    mbar_init(&pipe->r_bar, kFEpiThreads / 2);
+    for (int t = 0; t < 2; ++t) { mbar_init(&pipe->q_bar[t], 1); mbar_init(&pipe->o_bar[t], kFEpiThreads / 2); }
     mbar_fence_init();
   }
   if (warp == kFMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     Prof pf{kProf && a.prof == 1 && lane == 0, 0};
     Cn.pf = pf;
     long long acc_a = 0;
-    uint32_t g = 0, rr = 0;
+    uint32_t g = 0, rr = 0, po[2] = {0, 0};
     const long long t_begin = clock64();
     auto wait_a = [&]() { pf.start(); mbar_wait(&pipe->a_bar[0], g & 1); pf.stop(acc_a); tc_fence_after(); };
     auto done = [&]() { if (elect_one()) mma_commit(&pipe->d_bar[0]); __syncwarp(); ++g; };
@@ -348,17 +353,22 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
-        wait_a(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); done();           // q|k|v of head 0
-#pragma unroll 1
-        for (int h = 0; h < 4; ++h) {
-          if (h < 3) {                                                             // R copied out by the epilogue:
-            mbar_wait(&pipe->r_bar, rr & 1); ++rr; tc_fence_after();               // q|k|v of head h+1 overlaps the
-            gemm(K10{}, N192{}, kT_ColR, kT_ColY, false);                          // attention math of head h
-          }
-          wait_a();
-          gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                              // x += o_h Wo_h^T
-          done();
-        }
+        // Attention block.  The epilogue warps form two teams (A: heads 0, 2; B: heads 1, 3) that run their
+        // heads concurrently, so the issue slots one team leaves empty in its barrier / latency stalls are
+        // filled by the other.  R is single: the next head's q|k|v is issued as soon as the team that owns
+        // the current one has copied it out (r_bar); each team's output has its own half of OT.
+        auto wait_r = [&]() { mbar_wait(&pipe->r_bar, rr & 1); ++rr; tc_fence_after(); };
+        auto wait_o = [&](int t) { pf.start(); mbar_wait(&pipe->o_bar[t], po[t] & 1); ++po[t]; pf.stop(acc_a); tc_fence_after(); };
+        auto commit_q = [&](int t) { if (elect_one()) mma_commit(&pipe->q_bar[t]); __syncwarp(); };
+        wait_a(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // q|k|v of head 0 -> team A
+        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 1 -> team B
+        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                         // x += o_0 Wo_0^T
+        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // head 2 -> team A
+        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);                    // x += o_1 Wo_1^T
+        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 3 -> team B
+        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                         // x += o_2 Wo_2^T
+        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);                    // x += o_3 Wo_3^T
+        done();
         wait_a(); gemm(K10{}, N128{}, kT_ColR, kT_ColY, false); done();            // FF hidden
         wait_a(); gemm(K8{}, N160{}, kT_ColX, kT_ColO, true); done();              // x += gelu(.) W2^T
       }
@@ -373,12 +383,9 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     // ================= epilogue warps =================
     reg_inc<104>();
     const int r = tid & 127, q = tid >> 7;
-    uint8_t* KX = smem + kT_KX;
-    uint8_t* VX = smem + kT_VX;
-    float* PD = reinterpret_cast<float*>(smem + kT_PD);
     float* LS = reinterpret_cast<float*>(smem + kT_LS);
     const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t g = 0;
+    uint32_t g = 0, pq = 0;
     Prof pf{kProf && a.prof == 1 && tid == 0, 0};
     long long acc_d = 0, acc_tl = 0, n_tiles = 0;
     long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // publish, bar1, dots, bar2, softmax+o, LN2, GELU, LN1/final
@@ -428,104 +435,124 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
         const float* fp = FP + l * kTLayerFloats;   // ln1_g ln1_b pend_in ln2_g ln2_b pend_mid b1
+        {
+          // ---- attention (lib/transformer.py:59-71).  Two teams of 8 warps (team = q >> 1: A = heads 0, 2;
+          // B = heads 1, 3) work on different heads at the same time.  R = [q | k | v] of one head, 64 columns
+          // each; thread (r, hf = q & 1) owns head dims [32 hf, 32 hf + 32) of its row.  It keeps its own q, k, v
+          // slices in registers and publishes k and v as fp16 (unit-swizzled 128-byte rows) for the V - 1
+          // partner rows of its point; softmax and the weighted sum are symmetric in the key order, so keys
+          // are visited as (self, partner 1, ..).
+          const int team = q >> 1, hf = q & 1;
+          uint8_t* KXt = smem + team * kT_TeamBytes + kT_KX;
+          uint8_t* VXt = smem + team * kT_TeamBytes + kT_VX;
+          float* PDt = reinterpret_cast<float*>(smem + team * kT_TeamBytes + kT_PD);
 #pragma unroll 1
-        for (int h = 0; h < 4; ++h) {
-          wait_d();
-          pf.start();
-          // ---- attention of head h (lib/transformer.py:59-71): R = [q | k | v], 64 columns each; this
-          // thread owns head dims [16 q, 16 q + 16) of its row.  It keeps its own q, k, v slices in
-          // registers (fp32) and publishes k (fp32) and v (fp16) in unit-swizzled rows for the V - 1
-          // partner rows of its point; nobody reads back its own row.  Softmax and the weighted sum are symmetric in the key order, so
-          // keys are visited as (self, partner 1, ..) -- no per-lane key index is needed.
-          float qv[16], kk[16], vv[16];
-          tmem_ld_x16(tl + kT_ColR + 64 + 16 * q, kk);
-          tmem_ld_x16(tl + kT_ColR + 128 + 16 * q, vv);
-          tmem_ld_x16(tl + kT_ColR + 16 * q, qv);
-          tmem_ld_wait();
-          if (h < 3) { tc_fence_before(); mbar_arrive(&pipe->r_bar); }   // R is free: the next head's q|k|v may land
-          {
-            uint8_t* kd = KX + r * 256;
+          for (int hh = 0; hh < 2; ++hh) {
+            pf.start();
+            mbar_wait(&pipe->q_bar[team], pq & 1);
+            ++pq;
+            tc_fence_after();
+            pf.stop(acc_d);
+            float qv[32];
+            __half2 vh[16];
+            {
+              float kk[32];
+              tmem_ld_x32(tl + kT_ColR + 64 + 32 * hf, kk);
+              tmem_ld_x32(tl + kT_ColR + 32 * hf, qv);
+              tmem_ld_wait();
+              uint8_t* kd = KXt + r * 128;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<float4*>(kd + (((4 * q + u) ^ (r & 15)) << 4)) = make_float4(kk[4 * u], kk[4 * u + 1], kk[4 * u + 2], kk[4 * u + 3]);
-            uint8_t* vd = VX + r * 128;
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(kd + (((4 * hf + u) ^ (r & 7)) << 4)) =
+                    make_uint4(pack_h2(kk[8 * u], kk[8 * u + 1]), pack_h2(kk[8 * u + 2], kk[8 * u + 3]),
+                               pack_h2(kk[8 * u + 4], kk[8 * u + 5]), pack_h2(kk[8 * u + 6], kk[8 * u + 7]));
+              float d[4] = {0.f, 0.f, 0.f, 0.f};      // own key, fp32
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-              *reinterpret_cast<uint4*>(vd + (((2 * q + u) ^ (r & 7)) << 4)) =
-                  make_uint4(pack_h2(vv[8 * u], vv[8 * u + 1]), pack_h2(vv[8 * u + 2], vv[8 * u + 3]),
-                             pack_h2(vv[8 * u + 4], vv[8 * u + 5]), pack_h2(vv[8 * u + 6], vv[8 * u + 7]));
-          }
-          {   // own key while the partners' rows are still being published
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              d[0] = fmaf(qv[4 * u], kk[4 * u], d[0]); d[1] = fmaf(qv[4 * u + 1], kk[4 * u + 1], d[1]);
-              d[2] = fmaf(qv[4 * u + 2], kk[4 * u + 2], d[2]); d[3] = fmaf(qv[4 * u + 3], kk[4 * u + 3], d[3]);
+              for (int u = 0; u < 8; ++u) {
+                d[0] = fmaf(qv[4 * u], kk[4 * u], d[0]); d[1] = fmaf(qv[4 * u + 1], kk[4 * u + 1], d[1]);
+                d[2] = fmaf(qv[4 * u + 2], kk[4 * u + 2], d[2]); d[3] = fmaf(qv[4 * u + 3], kk[4 * u + 3], d[3]);
+              }
+              PDt[(hf * 128 + r) * 4] = (d[0] + d[1]) + (d[2] + d[3]);
             }
-            PD[(q * 128 + r) * 4] = (d[0] + d[1]) + (d[2] + d[3]);
-          }
-          pf.stop(sec[0]);
-          f_epi_bar();            // a point's rows may sit in different lane quarters: CTA-wide
-          pf.stop(sec[1]);
-          // partial dots with the partner keys over this thread's 16 of the 64 head dims (fp32 accumulation)
+            {
+              float vv[32];
+              tmem_ld_x32(tl + kT_ColR + 128 + 32 * hf, vv);
+              tmem_ld_wait();
+              if (team + 2 * hh < 3) { tc_fence_before(); mbar_arrive(&pipe->r_bar); }   // R is free: the next head's q|k|v may land
+              uint8_t* vd = VXt + r * 128;
 #pragma unroll
-          for (int j = 1; j < V; ++j) {
-            const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
-            const uint8_t* src = KX + rj * 256;
-            float4 kp[4];
+              for (int i = 0; i < 16; ++i) vh[i] = __floats2half2_rn(vv[2 * i], vv[2 * i + 1]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)      // all loads of the row first: one exposed smem latency per row
-              kp[u] = *reinterpret_cast<const float4*>(src + (((4 * q + u) ^ (rj & 15)) << 4));
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              d[0] = fmaf(qv[4 * u], kp[u].x, d[0]); d[1] = fmaf(qv[4 * u + 1], kp[u].y, d[1]);
-              d[2] = fmaf(qv[4 * u + 2], kp[u].z, d[2]); d[3] = fmaf(qv[4 * u + 3], kp[u].w, d[3]);
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(vd + (((4 * hf + u) ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(&vh[4 * u]);
             }
-            PD[(q * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
-          }
-          pf.stop(sec[2]);
-          f_row_bar(warp);
-          pf.stop(sec[3]);
-          float w[V];
-          float mx = -1e30f;
+            pf.stop(sec[0]);
+            named_bar_sync(6 + team, kFEpiThreads / 2);      // a point's rows may sit in different lane quarters: team-wide
+            pf.stop(sec[1]);
+            // partial dots with the partner keys over this thread's 32 of the 64 head dims (fp32 accumulation)
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            w[j] = ((PD[r * 4 + j] + PD[(128 + r) * 4 + j]) + (PD[(256 + r) * 4 + j] + PD[(384 + r) * 4 + j])) * 0.125f;   // dim_head ** -0.5
-            mx = fmaxf(mx, w[j]);
-          }
-          float den = 0.f;
+            for (int j = 1; j < V; ++j) {
+              const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
+              const uint8_t* src = KXt + rj * 128;
+              uint4 kp[4];
 #pragma unroll
-          for (int j = 0; j < V; ++j) { w[j] = __expf(w[j] - mx); den += w[j]; }
-          const float inv = 1.0f / den;
-          // o = sum_j softmax_j * v_j over this thread's 16 dims, accumulated as half2 (V terms;
-          // the result is rounded to bf16 for the out-projection anyway)
-          __half2 oh[8];
-          {
-            const __half2 w0 = __float2half2_rn(w[0] * inv);
+              for (int u = 0; u < 4; ++u) kp[u] = *reinterpret_cast<const uint4*>(src + (((4 * hf + u) ^ (rj & 7)) << 4));
+              float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) oh[i] = __hmul2(w0, __floats2half2_rn(vv[2 * i], vv[2 * i + 1]));
-          }
+              for (int u = 0; u < 4; ++u) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&kp[u]);
 #pragma unroll
-          for (int j = 1; j < V; ++j) {
-            const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
-            const __half2 wj = __float2half2_rn(w[j] * inv);
-            const uint8_t* src = VX + rj * 128;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint4 pkv = *reinterpret_cast<const uint4*>(src + (((2 * q + u) ^ (rj & 7)) << 4));
-              const __half2* h2 = reinterpret_cast<const __half2*>(&pkv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) oh[4 * u + i] = __hfma2(wj, h2[i], oh[4 * u + i]);
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __half22float2(h2[i]);
+                  d[(2 * i) & 3] = fmaf(qv[8 * u + 2 * i], f.x, d[(2 * i) & 3]);
+                  d[(2 * i + 1) & 3] = fmaf(qv[8 * u + 2 * i + 1], f.y, d[(2 * i + 1) & 3]);
+                }
+              }
+              PDt[(hf * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
             }
-          }
-          uint32_t pk[8];
+            pf.stop(sec[2]);
+            named_bar_sync(8 + 4 * team + (warp & 3), 64);    // the two threads of a row (warps w, w + 4 of the team)
+            pf.stop(sec[3]);
+            float w[V];
+            float mx = -1e30f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const float2 f = __half22float2(oh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
-          tmem_st_x8(tl + kT_ColO + 8 * q, pk);
-          tmem_st_wait();
-          pf.stop(sec[4]);
-          hand_over();
+            for (int j = 0; j < V; ++j) {
+              w[j] = (PDt[r * 4 + j] + PDt[(128 + r) * 4 + j]) * 0.125f;      // dim_head ** -0.5
+              mx = fmaxf(mx, w[j]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) { w[j] = __expf(w[j] - mx); den += w[j]; }
+            const float inv = 1.0f / den;
+            // o = sum_j softmax_j * v_j over this thread's 32 dims, accumulated as half2 (V terms; the result is
+            // rounded to bf16 for the out-projection anyway)
+            {
+              const __half2 w0 = __float2half2_rn(w[0] * inv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) vh[i] = __hmul2(w0, vh[i]);
+            }
+#pragma unroll
+            for (int j = 1; j < V; ++j) {
+              const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
+              const __half2 wj = __float2half2_rn(w[j] * inv);
+              const uint8_t* src = VXt + rj * 128;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint4 pkv = *reinterpret_cast<const uint4*>(src + (((4 * hf + u) ^ (rj & 7)) << 4));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&pkv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vh[4 * u + i] = __hfma2(wj, h2[i], vh[4 * u + i]);
+              }
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(vh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
+            tmem_st_u16(tl + kT_ColO + 32 * team + 16 * hf, pk);
+            tmem_st_wait();
+            pf.stop(sec[4]);
+            tc_fence_before();
+            mbar_arrive(&pipe->o_bar[team]);
+          }
         }
         {
           // ---- x (+ deferred biases) -> LN2 -> YT
