@@ -68,6 +68,7 @@ struct Pipe {            // barriers of one CTA (in dynamic smem)
   uint64_t r_bar;       // T kernel: "scratch accumulator R has been copied out" (early release)
   uint64_t q_bar[2];    // T kernel: "q|k|v of this team's next head is in R" (tcgen05.commit)
   uint64_t o_bar[2];    // T kernel: "this team's attention output is in its half of OT" (256 arrivals)
+  uint64_t w_bar[2];    // T kernel: "the out-projection of this team's first head has read its half of OT" (commit)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     mbar_init(&pipe->a_bar[0], kFEpiThreads);
     mbar_init(&pipe->d_bar[0], 1);
     mbar_init(&pipe->r_bar, kFEpiThreads / 2);
-    for (int t = 0; t < 2; ++t) { mbar_init(&pipe->q_bar[t], 1); mbar_init(&pipe->o_bar[t], kFEpiThreads / 2); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&pipe->q_bar[t], 1); mbar_init(&pipe->o_bar[t], kFEpiThreads / 2); mbar_init(&pipe->w_bar[t], 1); }
     mbar_fence_init();
   }
   if (warp == kFMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
@@ -310,10 +311,11 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
         const uint8_t* src = a.blob + (size_t)l * kTLayerBytes;
-        for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);                                   // qkv_0
-#pragma unroll 1
-        for (int h = 0; h < 3; ++h) { for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk); P.push(src, kWoChunk); }   // qkv_{h+1}, Wo_h
-        P.push(src, kWoChunk);                                                                 // Wo_3
+        // consumption order of the attention block: qkv_0 qkv_1 qkv_2 Wo_0 qkv_3 Wo_1 Wo_2 Wo_3
+        for (int c = 0; c < 9; ++c) P.push(src, kQkvChunk);
+        P.push(src, kWoChunk);
+        for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);
+        for (int c = 0; c < 3; ++c) P.push(src, kWoChunk);
         for (int c = 0; c < 3; ++c) P.push(src, kW1Chunk);
         for (int c = 0; c < 2; ++c) P.push(src, kW2Chunk);
       }
@@ -360,12 +362,13 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         auto wait_r = [&]() { mbar_wait(&pipe->r_bar, rr & 1); ++rr; tc_fence_after(); };
         auto wait_o = [&](int t) { pf.start(); mbar_wait(&pipe->o_bar[t], po[t] & 1); ++po[t]; pf.stop(acc_a); tc_fence_after(); };
         auto commit_q = [&](int t) { if (elect_one()) mma_commit(&pipe->q_bar[t]); __syncwarp(); };
+        auto commit_w = [&](int t) { if (elect_one()) mma_commit(&pipe->w_bar[t]); __syncwarp(); };
         wait_a(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // q|k|v of head 0 -> team A
         wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 1 -> team B
-        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                         // x += o_0 Wo_0^T
-        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // head 2 -> team A
-        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);                    // x += o_1 Wo_1^T
+        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // head 2 -> team A (waits in R while A finishes head 0)
+        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true); commit_w(0);            // x += o_0 Wo_0^T
         wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 3 -> team B
+        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true); commit_w(1);       // x += o_1 Wo_1^T
         wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                         // x += o_2 Wo_2^T
         wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);                    // x += o_3 Wo_3^T
         done();
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     const int r = tid & 127, q = tid >> 7;
     float* LS = reinterpret_cast<float*>(smem + kT_LS);
     const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t g = 0, pq = 0;
+    uint32_t g = 0, pq = 0, pw = 0;
     Prof pf{kProf && a.prof == 1 && tid == 0, 0};
     long long acc_d = 0, acc_tl = 0, n_tiles = 0;
     long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // publish, bar1, dots, bar2, softmax+o, LN2, GELU, LN1/final
@@ -449,6 +452,14 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
 #pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {
             pf.start();
+            if (hh == 1) {
+              // the team's second head may already be waiting in R: its exchange buffers are free only when every
+              // thread of the team is done with the first head, and its half of OT only when that head's
+              // out-projection has read it
+              named_bar_sync(6 + team, kFEpiThreads / 2);
+              mbar_wait(&pipe->w_bar[team], pw & 1);
+              ++pw;
+            }
             mbar_wait(&pipe->q_bar[team], pq & 1);
             ++pq;
             tc_fence_after();

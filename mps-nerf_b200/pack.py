@@ -4,8 +4,8 @@ Layout (bytes; every weight tile is K-major bf16 in SWIZZLE_128B chunks, see
 ``engine.pack_kmajor_sw128``), in the exact order the kernels stream it:
 
   transformer, per layer l (466 944 B):
-      qkv_0[3 chunks x 192 rows]; then for h = 0..2: qkv_{h+1}[3 x 192], Wo_h[1 x 160];
-      Wo_3[1 x 160]; W1[3 x 128]; W2[2 x 160]
+      qkv_0, qkv_1, qkv_2 [3 chunks x 192 rows each]; Wo_0 [1 x 160]; qkv_3; Wo_1; Wo_2; Wo_3;
+      W1[3 x 128]; W2[2 x 160]
       qkv_h rows = (q_h | k_h | v_h) = to_qkv rows 64h.., 256+64h.., 512+64h..   (K = 155 -> 192)
   MLP (1 441 792 B = 44 ring slots of 2 chunks of 128 rows x 128 B), every 256-output layer split
       into its two N-halves (output rows 0..127, then 128..255), each half 4 chunks (K = 256) per K part:
@@ -53,11 +53,11 @@ def pack_weights_bf16(net, device=None):
         qkv = [torch.cat([wqkv[64 * h:64 * h + 64], wqkv[256 + 64 * h:256 + 64 * h + 64],
                           wqkv[512 + 64 * h:512 + 64 * h + 64]], 0) for h in range(4)]
         out = [wo[:, 64 * h:64 * h + 64] for h in range(4)]
-        parts.append(pack_kmajor_sw128(qkv[0], 192, 192))
-        for h in range(3):            # q|k|v of head h+1 is streamed before Wo_h (its GEMM is issued first)
-            parts.append(pack_kmajor_sw128(qkv[h + 1], 192, 192))
-            parts.append(pack_kmajor_sw128(out[h], 160, 64))
-        parts.append(pack_kmajor_sw128(out[3], 160, 64))
+        # issue order of the attention block (two epilogue teams, csrc/dense_tc.cu): q|k|v of heads 0, 1, 2, then
+        # Wo_0, q|k|v of head 3, Wo_1, Wo_2, Wo_3
+        for item in ("q0", "q1", "q2", "o0", "q3", "o1", "o2", "o3"):
+            h = int(item[1])
+            parts.append(pack_kmajor_sw128(qkv[h], 192, 192) if item[0] == "q" else pack_kmajor_sw128(out[h], 160, 64))
         parts.append(pack_kmajor_sw128(w1, 128, 192))
         parts.append(pack_kmajor_sw128(w2, 160, 128))
         pend_in = pend.clone()
