@@ -454,11 +454,9 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
             pf.start();
             if (hh == 1) {
               // the team's second head may already be waiting in R: its exchange buffers are free only when every
-              // thread of the team is done with the first head, and its half of OT only when that head's
-              // out-projection has read it
+              // thread of the team is done with the first head (and its half of OT only when that head's
+              // out-projection has read it: w_bar, checked right before o is stored)
               named_bar_sync(6 + team, kFEpiThreads / 2);
-              mbar_wait(&pipe->w_bar[team], pw & 1);
-              ++pw;
             }
             mbar_wait(&pipe->q_bar[team], pq & 1);
             ++pq;
@@ -558,6 +556,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(vh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
+            if (hh == 1) { mbar_wait(&pipe->w_bar[team], pw & 1); ++pw; }     // (long complete by now)
             tmem_st_u16(tl + kT_ColO + 32 * team + 16 * hf, pk);
             tmem_st_wait();
             pf.stop(sec[4]);

@@ -83,6 +83,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // commit / bulk copies are issued from `if (elect_one()) {...}` inside warp-uniform control flow:
 // their operands then live in uniform registers instead of going through per-use R2UR round trips
 // (a single-lane `if (lane == 0)` branch makes every UTCHMMA a slow waterfall loop).
+// Ampere-style asynchronous 16-byte copy global -> shared (SASS LDGSTS): no destination registers, so a
+// prefetch cannot stall its issuer on a spill of the loaded data.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
