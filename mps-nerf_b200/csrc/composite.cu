@@ -18,6 +18,9 @@ __device__ __forceinline__ float wide_sigmoid(float x) {     // run_nerf_helpers
   return 1.0002f * (1.0f / (1.0f + expf(-x))) - 0.0001f;
 }
 
+// kPer = samples per lane, a compile-time bound so that the per-lane loops carry no dead iterations
+// (S = 64 -> 2); the kernel handles every S <= 32 kPer.
+template <int kPer>
 __global__ void __launch_bounds__(kK6Threads)
 composite_kernel(const float* __restrict__ raw, const float* __restrict__ rays, int64_t n_rays, int S,
                  const float* __restrict__ t_vals, const float* __restrict__ u, const float* __restrict__ z_vals,
@@ -34,12 +37,12 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ rays, 
     const float* u_row = u ? u + r * S : nullptr;
     const float* z_row = z_vals ? z_vals + r * S : nullptr;
     const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
-    float alpha[kMaxPerLane], zs[kMaxPerLane];
-    float4 c[kMaxPerLane];
+    float alpha[kPer], zs[kPer];
+    float4 c[kPer];
     float prod = 1.f;
     const int s0 = lane * per;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < kPer; ++k) {
       const int s = s0 + k;
       alpha[k] = 0.f; zs[k] = 0.f; c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < per && s < S) {
@@ -65,6 +68,30 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ rays, 
         prod *= (1.f - a + 1e-10f);
       }
     }
+    {
+      // rays on which no sample absorbs (every alpha exactly 0; most rays of a frame miss the body):
+      // weights 0, transmittance 1, sums 0, disp = 1 / max(1e-10, 0/0) = NaN -- what the general path produces
+      bool none = true;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) none = none && (alpha[k] == 0.f);
+      if (__all_sync(0xffffffffu, none)) {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const int s = s0 + k;
+          if (k < per && s < S) {
+            if (w_out) w_out[r * S + s] = 0.f;
+            if (ts_out) ts_out[r * S + s] = 1.f;
+          }
+        }
+        if (lane == 0) {
+          rgb_out[3 * r] = 0.f; rgb_out[3 * r + 1] = 0.f; rgb_out[3 * r + 2] = 0.f;
+          acc_out[r] = 0.f;
+          if (depth_out) depth_out[r] = 0.f;
+          disp_out[r] = __int_as_float(0x7fffffff);
+        }
+        continue;
+      }
+    }
     // exclusive product scan across lanes
     float incl = prod;
 #pragma unroll
@@ -76,7 +103,7 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ rays, 
     if (lane == 0) T = 1.f;
     float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < kPer; ++k) {
       const int s = s0 + k;
       if (k < per && s < S) {
         const float w = alpha[k] * T;
@@ -123,8 +150,11 @@ extern "C" int mpsnerf_composite(const float* raw, const float* rays, int64_t n_
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
   int64_t blocks = (n_rays * 32 + mps::kK6Threads - 1) / mps::kK6Threads;
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
-  mps::composite_kernel<<<(int)blocks, mps::kK6Threads, 0, (cudaStream_t)stream>>>(
-      raw, rays, n_rays, S, t_vals, u, z_vals, occupancy, rgb, disp, acc, depth, weights, trans);
+  const int per = (S + 31) / 32;
+#define MPS_K6(P) mps::composite_kernel<P><<<(int)blocks, mps::kK6Threads, 0, (cudaStream_t)stream>>>( \
+      raw, rays, n_rays, S, t_vals, u, z_vals, occupancy, rgb, disp, acc, depth, weights, trans)
+  if (per <= 1) MPS_K6(1); else if (per <= 2) MPS_K6(2); else if (per <= 4) MPS_K6(4); else MPS_K6(8);
+#undef MPS_K6
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
 }

@@ -13,16 +13,45 @@ constexpr int kK3Threads = 128;
 
 struct Xf { float m[12]; };   // 3x4 row-major
 
-// Sequential blend over the 24 joints; zero weights are skipped (adding +-0 never changes a
-// value), the j = 0 term always initialises.
-__device__ __forceinline__ void blend(const float (&w)[24], const float* __restrict__ A, Xf& M) {
+// Two blends with the same weights (sum_j w_j A0_j and sum_j w_j A1_j), sequential over the 24 joints in
+// joint order; zero weights are skipped (adding +-0 never changes a value), the
+// j = 0 term always initialises.  kNorm: the weights are first divided by their (sequential) sum
+// (lib/skinnning_batch.py:261-262).  The joint loop is rolled in groups of four (one 16-byte weight load per
+// group, transforms addressed in shared memory at run time): fully unrolled, the four blends of the kernel were
+// 2.7 K instructions of mostly skipped code and the kernel stalled on instruction fetch.
+template <bool kNorm>
+__device__ __forceinline__ void blend2(const float* __restrict__ skin_w, int v, const float* __restrict__ A0,
+                                       const float* __restrict__ A1, Xf& M0, Xf& M1) {
+  const float4* p = reinterpret_cast<const float4*>(skin_w + (size_t)v * 24);
+  float4 t = __ldg(p);
+  float s = 1.f;
+  if (kNorm) {
+    s = padd(padd(padd(t.x, t.y), t.z), t.w);
+#pragma unroll 1
+    for (int k = 1; k < 6; ++k) {
+      const float4 n = __ldg(p + k);
+      s = padd(padd(padd(padd(s, n.x), n.y), n.z), n.w);
+    }
+  }
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    float wv[4] = {t.x, t.y, t.z, t.w};
+    if (k < 5) t = __ldg(p + k + 1);
+    const float* a0 = A0 + 48 * k;
+    const float* a1 = A1 + 48 * k;
 #pragma unroll
-  for (int e = 0; e < 12; ++e) M.m[e] = pmul(w[0], A[e]);
+    for (int i = 0; i < 4; ++i) {
+      const float w = kNorm ? pdiv(wv[i], s) : wv[i];
+      if (i == 0 && k == 0) {
 #pragma unroll
-  for (int j = 1; j < 24; ++j) {
-    if (w[j] != 0.f) {
+        for (int e = 0; e < 12; ++e) { M0.m[e] = pmul(w, a0[e]); M1.m[e] = pmul(w, a1[e]); }
+      } else if (w != 0.f) {
 #pragma unroll
-      for (int e = 0; e < 12; ++e) M.m[e] = padd(M.m[e], pmul(w[j], A[j * 12 + e]));
+        for (int e = 0; e < 12; ++e) {
+          M0.m[e] = padd(M0.m[e], pmul(w, a0[12 * i + e]));
+          M1.m[e] = padd(M1.m[e], pmul(w, a1[12 * i + e]));
+        }
+      }
     }
   }
 }
@@ -51,15 +80,6 @@ __device__ __forceinline__ void apply_fwd(const Xf& M, float x, float y, float z
   ox = padd(padd(padd(pmul(M.m[0], x), pmul(M.m[1], y)), pmul(M.m[2], z)), M.m[3]);
   oy = padd(padd(padd(pmul(M.m[4], x), pmul(M.m[5], y)), pmul(M.m[6], z)), M.m[7]);
   oz = padd(padd(padd(pmul(M.m[8], x), pmul(M.m[9], y)), pmul(M.m[10], z)), M.m[11]);
-}
-
-__device__ __forceinline__ void load_weights(const float* __restrict__ skin_w, int v, float (&w)[24]) {
-  const float4* p = reinterpret_cast<const float4*>(skin_w + (size_t)v * 24);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    float4 t = __ldg(p + k);
-    w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
-  }
 }
 
 __global__ void __launch_bounds__(kK3Threads)
@@ -91,20 +111,17 @@ deform_project_kernel(const int32_t* __restrict__ act_pid, const int32_t* __rest
     const int64_t i = base + threadIdx.x;
     const bool valid = i < count;
     float cx = 0.f, cy = 0.f, cz = 0.f;
-    float w[24];
-    Xf M;
+    Xf M, M2;
     if (valid) {
       const int64_t a = first + i;
       const float qx = act_q[3 * a], qy = act_q[3 * a + 1], qz = act_q[3 * a + 2];
       if (identity_canonical) {                 // extract_mesh: canonical_pts = world_query_pts (:394-396)
         cx = qx; cy = qy; cz = qz;
       } else {
-        load_weights(skin_w, act_idx2[a], w);
-        blend(w, s_fr.A_tp, M);
+        blend2<false>(skin_w, act_idx2[a], s_fr.A_tp, s_fr.A_big_tp, M, M2);
         float tx, ty, tz;
         apply_inv(M, qx, qy, qz, tx, ty, tz);
-        blend(w, s_fr.A_big_tp, M);
-        apply_fwd(M, tx, ty, tz, cx, cy, cz);
+        apply_fwd(M2, tx, ty, tz, cx, cy, cz);
       }
     }
     // nearest template vertex (no radius guarantee: accept below safe_r2, else exact scan)
@@ -116,17 +133,10 @@ deform_project_kernel(const int32_t* __restrict__ act_pid, const int32_t* __rest
     }
     nn_brute_warp(h, g.sorted, valid && !(bd2 < h.safe_r2), cx, cy, cz, bd2, bidx);
     if (valid) {
-    load_weights(skin_w, bidx, w);
-    float s = w[0];
-#pragma unroll
-    for (int j = 1; j < 24; ++j) s = padd(s, w[j]);
-#pragma unroll
-    for (int j = 0; j < 24; ++j) w[j] = pdiv(w[j], s);          // :261-262
-    blend(w, s_fr.A_big_sp, M);
+    blend2<true>(skin_w, bidx, s_fr.A_big_sp, s_fr.A_sp, M, M2);   // weights normalised, :261-262
     float tx, ty, tz, sx, sy, sz;
     apply_inv(M, cx, cy, cz, tx, ty, tz);
-    blend(w, s_fr.A_sp, M);
-    apply_fwd(M, tx, ty, tz, sx, sy, sz);                       // smpl_src_pts
+    apply_fwd(M2, tx, ty, tz, sx, sy, sz);                      // smpl_src_pts
     const float* Ri = s_fr.Rinv_sp;
     const float wx = padd(padd(padd(pmul(sx, Ri[0]), pmul(sy, Ri[3])), pmul(sz, Ri[6])), s_fr.Th_sp[0]);   // :297-298
     const float wy = padd(padd(padd(pmul(sx, Ri[1]), pmul(sy, Ri[4])), pmul(sz, Ri[7])), s_fr.Th_sp[1]);
