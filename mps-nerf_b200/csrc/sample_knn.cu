@@ -87,7 +87,7 @@ sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const
       const float cxq = s_q[3 * t], cyq = s_q[3 * t + 1], czq = s_q[3 * t + 2];
       float bd2 = INF;
       int bidx = 0x7fffffff;
-      nn_search27(h, g.cell_start, g.sorted, cell_coord(cxq, h.ox, h.inv_cell), cell_coord(cyq, h.oy, h.inv_cell),
+      nn_search27_all(h, g.cell_start, g.sorted, cell_coord(cxq, h.ox, h.inv_cell), cell_coord(cyq, h.oy, h.inv_cell),
                   cell_coord(czq, h.oz, h.inv_cell), cxq, cyq, czq, bd2, bidx);
       s_d2[t] = bd2;
       s_idx[t] = bidx;
