@@ -233,13 +233,15 @@ class RenderEngine:
         H, W = img_all.shape[-2:]
         ctx = FrameContext()
         ctx.n_views = V
-        # Three independent branches (graph edges when captured): the encoder trunk on the current stream,
-        # K0 -> target-pose grid on one side stream, the template grid on another.  K0 and the grid builds
-        # are single-CTA kernels (~0.1 ms each) that would otherwise queue up behind the trunk.
+        # Four independent branches (graph edges when captured): the encoder trunk on the current stream, K0, the
+        # target-pose grid and the template grid on side streams.  K0 and the grid builds are single-CTA kernels
+        # (~0.1 ms each, 0.2 ms when they share their SM with the trunk's convolutions) that would otherwise queue
+        # up behind the trunk or behind each other; the target grid needs only the raw Th / R of the target pose
+        # (K0 copies them into the frame unchanged), so it does not wait for K0.
         main = torch.cuda.current_stream()
         sides = self._side.get(dev)
         if sides is None:
-            sides = self._side[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            sides = self._side[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
         tab = self._smpl_tables(smpl, dev)
         ctx.skin_w = tab["weights"]
         ctx.frame_dev = torch.empty(ctypes.sizeof(_lib.Frame), dtype=torch.uint8, device=dev)
@@ -258,11 +260,11 @@ class RenderEngine:
                                                  _lib.ptr(tab["J_regressor"]), _lib.ptr(tab["parents"]),
                                                  tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
                        "frame_prepare")
-            fptr = ctx.frame_dev.data_ptr()
-            _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, ctypes.c_void_p(fptr + _lib.Frame.Th_tp.offset),
-                                              ctypes.c_void_p(fptr + _lib.Frame.R_tp.offset), GRID_CELL_TARGET,
-                                              _lib.ptr(ctx.grid_tp), gb, _stream()), "grid_build(target)")
         with torch.cuda.stream(sides[1]):
+            # keep = [poses, shapes, R, Th](target), [poses, shapes, R, Th](source), R_all, T_all, K_all
+            _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, _lib.ptr(keep[3]), _lib.ptr(keep[2]), GRID_CELL_TARGET,
+                                              _lib.ptr(ctx.grid_tp), gb, _stream()), "grid_build(target)")
+        with torch.cuda.stream(sides[2]):
             _lib.check(lib.mpsnerf_grid_build(_lib.ptr(tverts), tverts.shape[0], None, None, GRID_CELL_TEMPLATE,
                                               _lib.ptr(ctx.grid_tv), gb, _stream()), "grid_build(template)")
         # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
