@@ -172,9 +172,10 @@ def run_ours(a):
         return R.render(rays=rays_d, near=near_d, far=far_d, sp_input=sp_d, tp_input=tp_d, **kw)
 
     def step_e2e():
+        # inputs start in pinned host memory: sp / tp are copied here, rays / near / far by render() itself (on a
+        # copy stream, under the frame preparation)
         sp, tp = to_dev(sp_h), to_dev(tp_h)
-        r, n, f = (t.to(dev, non_blocking=True) for t in (rays_h, near_h, far_h))
-        rgb, disp, acc, _ = R.render(rays=r, near=n, far=f, sp_input=sp, tp_input=tp, **kw)
+        rgb, disp, acc, _ = R.render(rays=rays_h, near=near_h, far=far_h, sp_input=sp, tp_input=tp, **kw)
         out_h[0].copy_(rgb, non_blocking=True)
         out_h[1].copy_(disp, non_blocking=True)
         out_h[2].copy_(acc, non_blocking=True)

@@ -99,7 +99,7 @@ def raw2outputs(raw, z_vals, rays_d, white_bkgd=False):
 
 
 def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, perturb=0.0, N_importance=0,
-                network_fine=None, white_bkgd=False, sp_input=None, tp_input=None, perturb_u=None):
+                network_fine=None, white_bkgd=False, sp_input=None, tp_input=None, perturb_u=None, _rays_ready=None):
     """ref :401-444.  ray_batch (B,C,8|11) = [o, d, near, far(, viewdirs)] -> dict of outputs.
 
     ``perturb_u`` (B,C,S) optionally supplies the stratified-sampling uniforms (otherwise drawn
@@ -121,6 +121,9 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, pert
     for b in range(B):
         sp, tp = _select(sp_input, b), _select(tp_input, b)
         ctx = net.frame_context(sp, tp)
+        if _rays_ready is not None:       # rays uploaded on the copy stream while the frame was being prepared
+            torch.cuda.current_stream(dev).wait_event(_rays_ready)
+            _rays_ready = None
         rays8 = ray_batch[b, :, :8].float().contiguous()
         per.append(eng.run(ctx, rays8=rays8, S=S, t_vals=t_vals, u=None if u is None else u[b],
                            occupancy=bool(global_args.occupancy)))
@@ -143,6 +146,16 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, pert
     }
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    s = _COPY_STREAMS.get(dev)
+    if s is None:
+        s = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
 def batchify_rays(rays_flat, chunk=1024 * 32, sp_input=None, tp_input=None, **kwargs):
     """ref :85-97: render in chunks of ``chunk`` rays and concatenate along the ray dim."""
     all_ret = {}
@@ -160,16 +173,30 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
     The whole ray set goes through the kernels at once (they chunk internally by active
     points); ``chunk`` only determines the width of ``extras['other_loss']`` (4 per chunk).
     """
-    rays_o, rays_d = rays[:, 0, ...], rays[:, 1, ...]
-    sh = rays_d.shape
-    B = sh[0]
-    rays_o = torch.reshape(rays_o, [B, -1, 3]).float()
-    rays_d = torch.reshape(rays_d, [B, -1, 3]).float()
-    near = torch.reshape(near, [B, -1, 1]).float()
-    far = torch.reshape(far, [B, -1, 1]).float()
-    packed = torch.cat([rays_o, rays_d, near, far], -1)
+    def pack(rays, near, far):
+        rays_o, rays_d = rays[:, 0, ...], rays[:, 1, ...]
+        B = rays_d.shape[0]
+        return torch.cat([torch.reshape(rays_o, [B, -1, 3]).float(), torch.reshape(rays_d, [B, -1, 3]).float(),
+                          torch.reshape(near, [B, -1, 1]).float(), torch.reshape(far, [B, -1, 1]).float()], -1)
+
+    sh = rays[:, 1, ...].shape
+    ready = None
+    if not rays.is_cuda and sp_input["img_all"].is_cuda:
+        # Host (ideally pinned) rays / near / far: uploaded and packed on a copy stream, so that the transfer
+        # overlaps the per-frame preparation (trunk, K0, grids), which needs only sp_input / tp_input.
+        dev = sp_input["img_all"].device
+        main = torch.cuda.current_stream(dev)
+        cs = _copy_stream(dev)
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            packed = pack(*(t.to(dev, non_blocking=True) for t in (rays, near, far)))
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        packed.record_stream(main)
+    else:
+        packed = pack(rays, near, far)
     n = packed.shape[1]
-    ret = render_rays(packed, sp_input=sp_input, tp_input=tp_input, **kwargs)
+    ret = render_rays(packed, sp_input=sp_input, tp_input=tp_input, _rays_ready=ready, **kwargs)
     nchunks = max(1, (n + chunk - 1) // chunk)
     ret["other_loss"] = torch.zeros(1, 4 * nchunks, device=packed.device)
     for k in ("rgb_map", "disp_map", "acc_map", "pts_mask", "raw"):

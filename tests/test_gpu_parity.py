@@ -451,3 +451,24 @@ def test_other_view_counts_against_oracle(n_views):
         assert (mask != (ref["pts_mask"][..., 0] > 0.5)).sum() <= 1 and mask.sum() > 200
         assert float(np.abs(rgb[0].cpu().numpy() - ref["rgb_map"]).max()) <= tol
         assert float(np.abs(acc[0].cpu().numpy() - ref["acc_map"]).max()) <= tol
+
+
+@pytest.mark.gpu
+def test_render_accepts_host_rays():
+    """render() with (pinned) host rays / near / far uploads them on its copy stream under the frame preparation;
+    the result is bit-identical to passing device tensors."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    sc = synthetic.make_scene("thuman", seed=3, H=128, W=128, novel_pose=True)
+    net = R.NetworkHandle(make_net(sc, synthetic.seeded_state_dict(0, 300.0), "bf16"))
+    ids = synthetic.inbox_ray_subset(sc, 300)
+    rays, near, far = synthetic.rays_tensor(sc, ids)
+    assert not rays.is_cuda
+    sp, tp = _cuda_dict(sc.sp_input), _cuda_dict(sc.tp_input)
+    kw = dict(sp_input=sp, tp_input=tp, network_fn=net, N_samples=32, perturb=False, use_viewdirs=True)
+    want = R.render(rays=rays.cuda(), near=near.cuda(), far=far.cuda(), **kw)
+    for _ in range(2):
+        got = R.render(rays=rays.pin_memory(), near=near.pin_memory(), far=far.pin_memory(), **kw)
+        torch.cuda.synchronize()
+        for k in range(3):
+            assert got[k].is_cuda and torch.equal(got[k].nan_to_num(-1.0), want[k].nan_to_num(-1.0))
+        assert torch.equal(got[3]["raw"], want[3]["raw"])
