@@ -96,6 +96,15 @@ int mpsnerf_grid_build(const float* verts, int n_verts, const float* Th, const f
 int mpsnerf_knn1(const float* query, int64_t n, const void* grid, float* d2_out,
                  int32_t* idx_out, void* stream);
 
+/* Mesh-extraction post-step on the density grid (replaces extract_thuman_mesh.py:125-158: shifted_softplus,
+ * knn_points K=1 mask, knn_points K=5 mean-normal inside/outside test, occupancy override).  One brute-force
+ * pass over the n_verts vertices per point keeps the five nearest (pinned d2, ties -> lowest index).
+ * raw: (n, raw_stride) floats, channel 3 = density logit; occupancy (n); optional outputs (may be NULL):
+ * pts_mask (n) int32, outside (n) uint8, idx5 (n,5) int32 sorted by (d2, index), d2_nearest (n). */
+int mpsnerf_occupancy_fix(const float* pts, int64_t n, const float* verts, const float* normals,
+                          int32_t n_verts, const float* raw, int32_t raw_stride, float* occupancy,
+                          int32_t* pts_mask, uint8_t* outside, int32_t* idx5, float* d2_nearest, void* stream);
+
 /* ---- K1: stratified sampling + world->SMPL + human-region mask + argmin + compaction ---
  * Replaces render_rays sampling (run_nerf_batch.py:406-424), run_network flattening
  * (:42-52) and SKinningBatch.forward steps 2,4 (lib/skinnning_batch.py:345-365).

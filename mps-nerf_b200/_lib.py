@@ -37,6 +37,8 @@ SIGNATURES = {
     "mpsnerf_grid_bytes": (c_size_t, [c_int]),
     "mpsnerf_grid_build": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
     "mpsnerf_knn1": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_occupancy_fix": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_sample_knn": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),

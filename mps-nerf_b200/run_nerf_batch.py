@@ -41,6 +41,8 @@ class NetworkHandle(nn.Module):
         self.module = module
 
     def forward(self, sp_input, tp_input, pts, viewdirs=None):
+        if pts.dim() == 2:      # extract_thuman_mesh.py:122: flat (P,3) points with the DataLoader-batched dicts
+            return self.module(sp_input, tp_input, pts, None)
         outs = []
         for b in range(pts.shape[0]):
             outs.append(self.module(_select(sp_input, b), _select(tp_input, b), pts[b], None))

@@ -4,6 +4,8 @@ integer outputs (mask, vertex indices) bit-exact; fp32 option rgb <= 1e-4; bf16 
 and PSNR >= 45 dB."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -472,3 +474,61 @@ def test_render_accepts_host_rays():
         for k in range(3):
             assert got[k].is_cuda and torch.equal(got[k].nan_to_num(-1.0), want[k].nan_to_num(-1.0))
         assert torch.equal(got[3]["raw"], want[3]["raw"])
+
+
+@pytest.mark.gpu
+def test_mesh_post_kernel_against_oracle_and_golden():
+    """csrc/occupancy.cu (one brute-force pass, five nearest in registers) against the oracle and the
+    reference-generated golden: mask and the five neighbour indices bit-exact, occupancy to fp32 rounding."""
+    from mpsnerf_b200 import extract_thuman_mesh as X
+    from oracle import occupancy as OC
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mesh_post.npz"))
+    flat, raw = torch.from_numpy(g["flat"]).cuda(), torch.from_numpy(g["raw"]).cuda()
+    nrm = torch.from_numpy(g["normals"])
+    occ, mask, outside, idx5, d2 = X.occupancy_post(flat, raw, torch.from_numpy(g["verts"]), g["faces"], want_debug=True, normals=nrm)
+    torch.cuda.synchronize()
+    o = OC.occupancy_post(g["flat"], g["raw"], g["verts"], normals=g["normals"])
+    assert np.array_equal(mask.cpu().numpy(), o["pts_mask"])
+    assert np.array_equal(mask.cpu().numpy().reshape(g["pts_mask"].shape), g["pts_mask"])
+    assert np.array_equal(idx5.cpu().numpy().astype(np.int64), g["vert_ids"])
+    d5, _ = OC.knn5(g["flat"], g["verts"])
+    assert np.array_equal(d2.cpu().numpy(), d5[:, 0])
+    sure = np.abs(o["dot"]) > 1e-5
+    assert np.array_equal(outside.cpu().numpy().astype(bool)[sure], g["outside_msk"].reshape(-1)[sure])
+    np.testing.assert_allclose(occ.cpu().numpy()[sure], g["occupancy"].reshape(-1)[sure], rtol=2e-6, atol=1e-6)
+    # ragged sizes / fewer than one tile of vertices / a single point
+    for n, nv in ((1, 7), (257, 2049), (1000, 5)):
+        rng = np.random.RandomState(n)
+        f = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        v = rng.uniform(-1, 1, (nv, 3)).astype(np.float32)
+        fc = rng.randint(0, nv, (3 * nv, 3))
+        r = rng.normal(0, 3, (n, 4)).astype(np.float32)
+        nr = rng.normal(0, 1, (nv, 3)).astype(np.float32)
+        got = X.occupancy_post(torch.from_numpy(f).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(v), fc, want_debug=True,
+                               normals=torch.from_numpy(nr))
+        want = OC.occupancy_post(f, r, v, normals=nr)
+        assert np.array_equal(got[3].cpu().numpy().astype(np.int64), want["idx5"])
+        assert np.array_equal(got[1].cpu().numpy(), want["pts_mask"])
+    assert X.occupancy_post(flat[:0], raw[:0], torch.from_numpy(g["verts"]), g["faces"]).numel() == 0
+
+
+@pytest.mark.gpu
+def test_estimate_occupancy_volume():
+    """The mirrored per-frame block (grid -> network -> post-step) on a coarse grid: shape, value set outside the
+    mask, and agreement of the in-mask densities with a direct network query."""
+    from mpsnerf_b200 import extract_thuman_mesh as X, run_nerf_batch as R, synthetic
+    sc = synthetic.make_scene("thuman", seed=2, H=128, W=128, novel_pose=True)
+    net = R.NetworkHandle(make_net(sc, synthetic.seeded_state_dict(0, 300.0), "bf16"))
+    sp, tp = _cuda_dict(sc.sp_input), _cuda_dict(sc.tp_input)
+    occ, START, SIZE, RANGE = X.estimate_occupancy(net, sp, tp, sc.smpl["f"], can_flag=False, n=24, chunk=5000)
+    assert occ.shape == (24, 24, 24) and tuple(RANGE) == (24, 24, 24)
+    q, _, _, _ = X.grid_points(False, 24)
+    flat = torch.from_numpy(q.reshape(-1, 3)).cuda()
+    raw = net(sp, tp, flat, torch.zeros_like(flat))[0, ..., 0:4]
+    verts = tp["vertices"].reshape(-1, 3)
+    d2 = torch.cdist(flat, verts).min(dim=1).values ** 2
+    inmask = (d2 < 0.05 ** 2 * 0.98).cpu().numpy()
+    want = torch.nn.functional.softplus(raw[:, 3] - 1).cpu().numpy()
+    np.testing.assert_allclose(occ.reshape(-1)[inmask], want[inmask], rtol=1e-5, atol=1e-6)
+    far = (d2 > 0.05 ** 2 * 1.02).cpu().numpy()
+    assert set(np.unique(occ.reshape(-1)[far])) <= {0.0, 100.0}
