@@ -397,44 +397,67 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     auto wait_d = [&]() { pf.start(); mbar_wait(&pipe->d_bar[0], g & 1); pf.stop(acc_d); ++g; tc_fence_after(); };
     constexpr int rows = ppt * V;
     const int p0 = (r < rows) ? (r / V) * V : 0;      // first row of this row's point (attention partners)
-    uint4 xn[5];                                       // this thread's 40 token columns (fp16) of the next tile
-    auto load_tokens = [&](int64_t tile) {
+    // The next tile's tokens (this thread's 40 fp16 columns, 5 x 16 B) are staged asynchronously (LDGSTS) in the
+    // attention exchange buffers, which are idle between the last attention block of a tile and the first one of
+    // the next ([unit][thread] layout, conflict-free), and picked up into registers when they are needed.
+    uint8_t* xstage = smem + tid * 16;
+    static_assert(5 * kFEpiThreads * 16 <= 2 * kT_TeamBytes, "token staging lives in the exchange buffers");
+    auto stage_tokens = [&](int64_t tile) {
       const int64_t row = min((tile * ppt + min(r, rows - 1) / V) * V + r % V, a.count * V - 1);
       const uint4* src = reinterpret_cast<const uint4*>(a.tokens + row * (int64_t)kTokLd + 40 * q);
 #pragma unroll
-      for (int c = 0; c < 5; ++c) xn[c] = __ldg(src + c);
+      for (int c = 0; c < 5; ++c) cp_async16(xstage + c * (kFEpiThreads * 16), src + c);
+      cp_async_commit();
     };
-    bool first = true;
+    uint4 xn[5];
+    auto fetch_staged = [&]() {
+      cp_async_wait_all();
+#pragma unroll
+      for (int c = 0; c < 5; ++c) xn[c] = *reinterpret_cast<const uint4*>(xstage + c * (kFEpiThreads * 16));
+    };
+    auto unpack_tokens = [&](float (&x)[40]) {
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&xn[c]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h2[i]); x[8 * c + 2 * i] = f.x; x[8 * c + 2 * i + 1] = f.y; }
+      }
+    };
+    auto store_x = [&](const float (&x)[40]) {
+      uint32_t xb[40];
+#pragma unroll
+      for (int c = 0; c < 40; ++c) xb[c] = __float_as_uint(x[c]);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) tmem_st_x8(tl + kT_ColX + 40 * q + 8 * i, *reinterpret_cast<const uint32_t(*)[8]>(&xb[8 * i]));
+    };
+    // LN1 of layer 0 for the staged tile -> YT, and the hand-over that lets its first q|k|v GEMM start
+    auto open_tile = [&]() {
+      fetch_staged();
+      float x[40];
+      unpack_tokens(x);
+      ln_to_tmem(x, nullptr, FP, FP + 160, LS, r, q, warp, tl);
+      hand_over();
+    };
+
+    if (cid * kC < ntiles) {
+      // first tile of this CTA: tokens -> LN1 -> YT, tokens -> X.  Every later tile is opened inside the previous
+      // one (below), under its last GEMM.
+      pf.start();
+      stage_tokens(cid * kC + crank);
+      open_tile();
+      float x[40];
+      unpack_tokens(x);
+      store_x(x);
+      tmem_st_wait();
+      pf.stop(acc_tl);
+    }
 
     for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
       const int64_t tile = tbase + crank;              // tile >= ntiles: all rows invalid
       const int64_t pnt = tile * ppt + r / V;
       const int tok = r % V;
       const bool valid = (r < rows) && (pnt < a.count);
-      {
-        // ---- tile load: tokens -> X (TMEM), LN1 of layer 0 -> YT.  The tokens were fetched into xn while
-        // the previous tile's last GEMM ran (rows past the end are clamped: rows are independent and
-        // never written); only the first tile pays the global latency here.
-        pf.start();
-        if (first) { load_tokens(tile); first = false; }
-        float x[40];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const __half2* h2 = reinterpret_cast<const __half2*>(&xn[c]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h2[i]); x[8 * c + 2 * i] = f.x; x[8 * c + 2 * i + 1] = f.y; }
-        }
-        {
-          uint32_t xb[40];
-#pragma unroll
-          for (int c = 0; c < 40; ++c) xb[c] = __float_as_uint(x[c]);
-#pragma unroll
-          for (int i = 0; i < 5; ++i) tmem_st_x8(tl + kT_ColX + 40 * q + 8 * i, *reinterpret_cast<const uint32_t(*)[8]>(&xb[8 * i]));
-        }
-        ln_to_tmem(x, nullptr, FP, FP + 160, LS, r, q, warp, tl);
-        pf.stop(acc_tl);
-        hand_over();
-      }
+      const bool has_next = tbase + ncl * kC < ntiles;
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
         const float* fp = FP + l * kTLayerFloats;   // ln1_g ln1_b pend_in ln2_g ln2_b pend_mid b1
@@ -567,6 +590,8 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         {
           // ---- x (+ deferred biases) -> LN2 -> YT
           wait_d();
+          // every thread of both teams is past its attention: the exchange buffers are free for the staging
+          if (l == 1 && has_next) stage_tokens(tile + ncl * kC);
           pf.start();
           float x[40];
           load_x40(tl + kT_ColX + 40 * q, x);
@@ -595,7 +620,12 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
           hand_over();
         }
         {
-          if (l == 1 && tbase + ncl * kC < ntiles) load_tokens(tile + ncl * kC);   // in flight during the last GEMM
+          // Last layer: the next tile is opened first -- its LN1 needs only the staged tokens and YT, which the FF
+          // hidden GEMM has finished reading -- so that the tensor pipe runs its first q|k|v GEMM right behind this
+          // tile's last GEMM, while the epilogue writes this tile's output.  X is overwritten with the next tile's
+          // tokens only after it has been read; the first GEMM that accumulates into X (Wo of head 0) is issued
+          // after every thread of both teams has arrived at r_bar / o_bar, i.e. after these stores.
+          if (l == 1 && has_next) { pf.start(); open_tile(); pf.stop(acc_tl); }
           wait_d();
           pf.start();
           float x[40];
@@ -605,15 +635,22 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
             ln_to_tmem(x, f1 + 320, f1, f1 + 160, LS, r, q, warp, tl);
             pf.stop(sec[7]);
             hand_over();
-          } else if (valid && tok < 2) {
-            // ---- output tokens 0 (density branch) and 1 (colour branch), lib/skinnning_batch.py:441-442
-            const float4* p4 = reinterpret_cast<const float4*>(FP + 2 * kTLayerFloats + 40 * q);
-            uint4* dst = reinterpret_cast<uint4*>((tok == 0 ? a.tok0 : a.tok1) + pnt * kTokLd + 40 * q);
+          } else {
+            if (valid && tok < 2) {
+              // ---- output tokens 0 (density branch) and 1 (colour branch), lib/skinnning_batch.py:441-442
+              const float4* p4 = reinterpret_cast<const float4*>(FP + 2 * kTLayerFloats + 40 * q);
+              uint4* dst = reinterpret_cast<uint4*>((tok == 0 ? a.tok0 : a.tok1) + pnt * kTokLd + 40 * q);
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              const float4 pa = p4[2 * c], pb = p4[2 * c + 1];
-              dst[c] = make_uint4(pack_bf16x2(x[8 * c] + pa.x, x[8 * c + 1] + pa.y), pack_bf16x2(x[8 * c + 2] + pa.z, x[8 * c + 3] + pa.w),
-                                  pack_bf16x2(x[8 * c + 4] + pb.x, x[8 * c + 5] + pb.y), pack_bf16x2(x[8 * c + 6] + pb.z, x[8 * c + 7] + pb.w));
+              for (int c = 0; c < 5; ++c) {
+                const float4 pa = p4[2 * c], pb = p4[2 * c + 1];
+                dst[c] = make_uint4(pack_bf16x2(x[8 * c] + pa.x, x[8 * c + 1] + pa.y), pack_bf16x2(x[8 * c + 2] + pa.z, x[8 * c + 3] + pa.w),
+                                    pack_bf16x2(x[8 * c + 4] + pb.x, x[8 * c + 5] + pb.y), pack_bf16x2(x[8 * c + 6] + pb.z, x[8 * c + 7] + pb.w));
+              }
+            }
+            if (has_next) {
+              unpack_tokens(x);
+              store_x(x);
+              tmem_st_wait();
             }
           }
         }
