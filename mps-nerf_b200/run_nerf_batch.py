@@ -149,6 +149,31 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, pert
 
 
 _COPY_STREAMS = {}
+# what the render path reads from the input dicts (engine._prepare_frame, lib/skinnning_batch.frame_context)
+HOT_KEYS_SP = ("gender", "params", "t_vertices", "img_all", "K_all", "R_all", "T_all")
+HOT_KEYS_TP = ("gender", "params", "vertices")
+
+
+def _upload_hot(d, keys, dev):
+    """Device copy of the entries of a host input dict that the path reads (asynchronous for pinned tensors);
+    everything else in the dataset dict -- the target view's images, masks, indices -- stays on the host."""
+    def mv(v):
+        if torch.is_tensor(v):
+            return v.to(dev, non_blocking=True)
+        if isinstance(v, dict):
+            return {k: mv(x) for k, x in v.items()}
+        return v
+    return {k: mv(d[k]) for k in keys if k in d}
+
+
+def hot_input_bytes(sp_input, tp_input):
+    """Bytes render() uploads when it is handed host dicts (bench.py reports them as h2d_bytes_per_step)."""
+    def nbytes(v):
+        if torch.is_tensor(v):
+            return v.numel() * v.element_size()
+        return sum(nbytes(x) for x in v.values()) if isinstance(v, dict) else 0
+    return sum(nbytes(sp_input[k]) for k in HOT_KEYS_SP if k in sp_input) + \
+        sum(nbytes(tp_input[k]) for k in HOT_KEYS_TP if k in tp_input)
 
 
 def _copy_stream(dev):
@@ -183,6 +208,13 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
 
     sh = rays[:, 1, ...].shape
     ready = None
+    if not sp_input["img_all"].is_cuda:
+        # host dicts (ideally pinned): upload only what the path reads, on the current stream (the frame
+        # preparation needs them first); the rays follow on the copy stream below
+        if not torch.cuda.is_available():
+            raise RuntimeError("mpsnerf_b200 has no CPU path: a CUDA device is required")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        sp_input, tp_input = _upload_hot(sp_input, HOT_KEYS_SP, dev), _upload_hot(tp_input, HOT_KEYS_TP, dev)
     if not rays.is_cuda and sp_input["img_all"].is_cuda:
         # Host (ideally pinned) rays / near / far: uploaded and packed on a copy stream, so that the transfer
         # overlaps the per-frame preparation (trunk, K0, grids), which needs only sp_input / tp_input.

@@ -474,6 +474,13 @@ def test_render_accepts_host_rays():
         for k in range(3):
             assert got[k].is_cuda and torch.equal(got[k].nan_to_num(-1.0), want[k].nan_to_num(-1.0))
         assert torch.equal(got[3]["raw"], want[3]["raw"])
+    # host dicts as well: only the entries the path reads are uploaded
+    pin = lambda d: {k: (v.pin_memory() if torch.is_tensor(v) else pin(v) if isinstance(v, dict) else v) for k, v in d.items()}
+    kw_h = dict(kw, sp_input=pin(sc.sp_input), tp_input=pin(sc.tp_input))
+    got = R.render(rays=rays.pin_memory(), near=near.pin_memory(), far=far.pin_memory(), **kw_h)
+    torch.cuda.synchronize()
+    assert torch.equal(got[3]["raw"], want[3]["raw"]) and torch.equal(got[0], want[0])
+    assert R.hot_input_bytes(sc.sp_input, sc.tp_input) < sum(t.numel() * t.element_size() for t in (sc.sp_input["img_all"], sc.tp_input["img_all"]))
 
 
 @pytest.mark.gpu
