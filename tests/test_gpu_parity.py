@@ -273,10 +273,19 @@ def test_edge_cases():
     ids = synthetic.inbox_ray_subset(scene, 333)
     rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
     ref = R.render(rays=rays, near=near, far=far, **kw)
-    for S in (1, 37):
+    from oracle import oracle as O
+    for S in (1, 37, 128, 200):      # one to seven samples per lane of the compositing warp
         kw2 = dict(kw, N_samples=S)
         out = R.render(rays=rays, near=near, far=far, **kw2)
         assert out[3]["raw"].shape == (1, 333, S, 4)
+        # compositing (K6, compiled per samples-per-lane count) against raw2outputs on the same raw
+        z = O.sample_z(scene.near[ids], scene.far[ids], S)
+        o_rgb, o_disp, o_acc, _, _ = O.raw2outputs(out[3]["raw"][0].cpu(), torch.from_numpy(z), torch.from_numpy(scene.rays_d[ids]))
+        np.testing.assert_allclose(out[0][0].cpu().numpy(), o_rgb.numpy(), atol=2e-5)
+        np.testing.assert_allclose(out[2][0].cpu().numpy(), o_acc.numpy(), atol=2e-5)
+        solid = o_acc.numpy() > 1e-3
+        np.testing.assert_allclose(out[1][0].cpu().numpy()[solid], o_disp.numpy()[solid], rtol=1e-3)
+        assert np.array_equal(np.isnan(out[1][0].cpu().numpy()), np.isnan(o_disp.numpy()))
     # chunk invariance: a sub-range rendered alone equals the same rays inside the larger call, bit for bit
     sub = R.render(rays=rays[:, :, 100:200], near=near[:, 100:200], far=far[:, 100:200], **kw)
     assert torch.equal(sub[0], ref[0][:, 100:200]) and torch.equal(sub[3]["raw"], ref[3]["raw"][:, 100:200])
