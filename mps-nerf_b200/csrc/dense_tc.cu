@@ -69,6 +69,8 @@ struct Pipe {            // barriers of one CTA (in dynamic smem)
   uint64_t q_bar[2];    // T kernel: "q|k|v of this team's next head is in R" (tcgen05.commit)
   uint64_t o_bar[2];    // T kernel: "this team's attention output is in its half of OT" (256 arrivals)
   uint64_t w_bar[2];    // T kernel: "the out-projection of this team's first head has read its half of OT" (commit)
+  uint64_t h_bar[2];    // T kernel: "half j (64 columns) of the FF hidden layer is in R" (commit)
+  uint64_t g_bar[2];    // T kernel: "GELU of hidden half j is in OT" (256 arrivals: the threads with q >> 1 == j)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -287,7 +289,8 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     mbar_init(&pipe->a_bar[0], kFEpiThreads);
     mbar_init(&pipe->d_bar[0], 1);
     mbar_init(&pipe->r_bar, kFEpiThreads / 2);
-    for (int t = 0; t < 2; ++t) { mbar_init(&pipe->q_bar[t], 1); mbar_init(&pipe->o_bar[t], kFEpiThreads / 2); mbar_init(&pipe->w_bar[t], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&pipe->q_bar[t], 1); mbar_init(&pipe->o_bar[t], kFEpiThreads / 2); mbar_init(&pipe->w_bar[t], 1);
+                                  mbar_init(&pipe->h_bar[t], 1); mbar_init(&pipe->g_bar[t], kFEpiThreads / 2); }
     mbar_fence_init();
   }
   if (warp == kFMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         P.push(src, kWoChunk);
         for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);
         for (int c = 0; c < 3; ++c) P.push(src, kWoChunk);
-        for (int c = 0; c < 3; ++c) P.push(src, kW1Chunk);
+        for (int c = 0; c < 6; ++c) P.push(src, kW1Chunk / 2);          // W1 rows 0..63 (3 chunks), then rows 64..127
         for (int c = 0; c < 2; ++c) P.push(src, kW2Chunk);
       }
     }
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     Prof pf{kProf && a.prof == 1 && lane == 0, 0};
     Cn.pf = pf;
     long long acc_a = 0;
-    uint32_t g = 0, rr = 0, po[2] = {0, 0};
+    uint32_t g = 0, rr = 0, po[2] = {0, 0}, pg = 0;
     const long long t_begin = clock64();
     auto wait_a = [&]() { pf.start(); mbar_wait(&pipe->a_bar[0], g & 1); pf.stop(acc_a); tc_fence_after(); };
     auto done = [&]() { if (elect_one()) mma_commit(&pipe->d_bar[0]); __syncwarp(); ++g; };
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
       }
     };
     using K10 = std::integral_constant<int, 10>; using K4 = std::integral_constant<int, 4>; using K8 = std::integral_constant<int, 8>;
-    using N192 = std::integral_constant<int, 192>; using N160 = std::integral_constant<int, 160>; using N128 = std::integral_constant<int, 128>;
+    using N192 = std::integral_constant<int, 192>; using N160 = std::integral_constant<int, 160>; using N128 = std::integral_constant<int, 128>; using N64 = std::integral_constant<int, 64>;
     for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
@@ -372,8 +375,22 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                         // x += o_2 Wo_2^T
         wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);                    // x += o_3 Wo_3^T
         done();
-        wait_a(); gemm(K10{}, N128{}, kT_ColR, kT_ColY, false); done();            // FF hidden
-        wait_a(); gemm(K8{}, N160{}, kT_ColX, kT_ColO, true); done();              // x += gelu(.) W2^T
+        // Feed-forward, pipelined in two halves of the hidden layer: hidden columns [0,64) are handed to the
+        // epilogue threads that own them (q < 2) while [64,128) is still being computed, and x += gelu(.) W2^T runs
+        // over the first half's K = 64 while the other threads are still in their GELU.
+        wait_a();
+        gemm(K10{}, N64{}, kT_ColR, kT_ColY, false);
+        if (elect_one()) mma_commit(&pipe->h_bar[0]);
+        __syncwarp();
+        gemm(K10{}, N64{}, kT_ColR + 64, kT_ColY, false);
+        if (elect_one()) mma_commit(&pipe->h_bar[1]);
+        __syncwarp();
+        pf.start(); mbar_wait(&pipe->g_bar[0], pg & 1); pf.stop(acc_a); tc_fence_after();
+        gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);
+        pf.start(); mbar_wait(&pipe->g_bar[1], pg & 1); pf.stop(acc_a); tc_fence_after();
+        ++pg;
+        gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);
+        done();
       }
     }
     if (pf.on) {
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     const int r = tid & 127, q = tid >> 7;
     float* LS = reinterpret_cast<float*>(smem + kT_LS);
     const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t g = 0, pq = 0, pw = 0;
+    uint32_t g = 0, pq = 0, pw = 0, ph = 0;
     Prof pf{kProf && a.prof == 1 && tid == 0, 0};
     long long acc_d = 0, acc_tl = 0, n_tiles = 0;
     long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // publish, bar1, dots, bar2, softmax+o, LN2, GELU, LN1/final
@@ -600,8 +617,12 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
           hand_over();
         }
         {
-          // ---- FF hidden: GELU(acc + b1) -> bf16 operand (K = 128 -> 64 packed columns)
-          wait_d();
+          // ---- FF hidden: GELU(acc + b1) -> bf16 operand (K = 128 -> 64 packed columns); per hidden half
+          pf.start();
+          mbar_wait(&pipe->h_bar[q >> 1], ph & 1);
+          ++ph;
+          tc_fence_after();
+          pf.stop(acc_d);
           pf.start();
           float t[32];
           tmem_ld_x32(tl + kT_ColR + 32 * q, t);
@@ -617,7 +638,8 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
           tmem_st_u16(tl + kT_ColO + 16 * q, pk);
           tmem_st_wait();
           pf.stop(sec[6]);
-          hand_over();
+          tc_fence_before();
+          mbar_arrive(&pipe->g_bar[q >> 1]);
         }
         {
           // Last layer: the next tile is opened first -- its LN1 needs only the staged tokens and YT, which the FF

@@ -5,7 +5,7 @@ Layout (bytes; every weight tile is K-major bf16 in SWIZZLE_128B chunks, see
 
   transformer, per layer l (466 944 B):
       qkv_0, qkv_1, qkv_2 [3 chunks x 192 rows each]; Wo_0 [1 x 160]; qkv_3; Wo_1; Wo_2; Wo_3;
-      W1[3 x 128]; W2[2 x 160]
+      W1 rows 0..63 [3 x 64], W1 rows 64..127 [3 x 64]; W2[2 x 160]
       qkv_h rows = (q_h | k_h | v_h) = to_qkv rows 64h.., 256+64h.., 512+64h..   (K = 155 -> 192)
   MLP (1 441 792 B = 44 ring slots of 2 chunks of 128 rows x 128 B), every 256-output layer split
       into its two N-halves (output rows 0..127, then 128..255), each half 4 chunks (K = 256) per K part:
@@ -58,7 +58,8 @@ def pack_weights_bf16(net, device=None):
         for item in ("q0", "q1", "q2", "o0", "q3", "o1", "o2", "o3"):
             h = int(item[1])
             parts.append(pack_kmajor_sw128(qkv[h], 192, 192) if item[0] == "q" else pack_kmajor_sw128(out[h], 160, 64))
-        parts.append(pack_kmajor_sw128(w1, 128, 192))
+        parts.append(pack_kmajor_sw128(w1[:64], 64, 192))       # the FF hidden layer is computed in two 64-row halves
+        parts.append(pack_kmajor_sw128(w1[64:128], 64, 192))
         parts.append(pack_kmajor_sw128(w2, 160, 128))
         pend_in = pend.clone()
         pend_mid = pend_in + _pad160(sd[p + "0.fn.fn.to_out.0.bias"])
