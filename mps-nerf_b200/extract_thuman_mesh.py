@@ -43,15 +43,30 @@ def compute_normal(vertices, faces):
     return norm
 
 
-def grid_points(can_flag=False, n=N):
-    """:95-115 -> (query_pts (n,n,n|n/4,3) float32 numpy, START, SIZE, RANGE)."""
+def grid_axes(can_flag=False, n=N):
+    """:95-112 -> (t_1, t_2, t_3 float64 numpy, START, SIZE, RANGE)."""
     if can_flag:
         t_1, t_2, t_3 = np.linspace(-1.0, 1.0, n), np.linspace(-1.0, 1.0, n), np.linspace(-0.25, 0.25, n // 4)
         START, SIZE, RANGE = np.array([-1.0, -1.0, -0.25]), np.array([2.0, 2.0, 0.5]), np.array([n, n, n // 4])
     else:
         t_1, t_2, t_3 = np.linspace(0.0, 2.0, n), np.linspace(0.6, 2.6, n), np.linspace(0.0, 2.0, n)
         START, SIZE, RANGE = np.array([0.0, 0.6, 0.0]), np.array([2.0, 2.0, 2.0]), np.array([n, n, n])
-    query_pts = np.stack(np.meshgrid(t_1, t_2, t_3), -1).astype(np.float32)
+    return t_1, t_2, t_3, START, SIZE, RANGE
+
+
+def grid_points(can_flag=False, n=N, device=None):
+    """:95-115 -> (query_pts (n,n,n|n/4,3) float32, START, SIZE, RANGE).
+
+    ``device=None``: numpy, literally ``np.stack(np.meshgrid(t_1, t_2, t_3), -1).astype(np.float32)``.
+    With a CUDA device the same array is assembled there by broadcasting the three float32-rounded axes
+    (meshgrid only replicates values; 'xy' indexing puts t_2 on the first axis), which avoids building and
+    uploading a 200 MB host array per frame."""
+    t_1, t_2, t_3, START, SIZE, RANGE = grid_axes(can_flag, n)
+    if device is None:
+        return np.stack(np.meshgrid(t_1, t_2, t_3), -1).astype(np.float32), START, SIZE, RANGE
+    a1, a2, a3 = (torch.from_numpy(t.astype(np.float32)).to(device) for t in (t_1, t_2, t_3))
+    shape = (len(t_2), len(t_1), len(t_3))
+    query_pts = torch.stack([a1[None, :, None].expand(shape), a2[:, None, None].expand(shape), a3[None, None, :].expand(shape)], -1)
     return query_pts, START, SIZE, RANGE
 
 
@@ -89,10 +104,10 @@ def estimate_occupancy(net_fn, sp_input, tp_input, faces, can_flag=False, n=N, c
     """The reference's per-frame block :92-158: grid -> network -> occupancy volume (numpy, as handed to
     marching cubes).  ``faces`` = SMPL ``f`` (:129-130)."""
     net = net_fn.module if hasattr(net_fn, "module") else net_fn
-    query_pts, START, SIZE, RANGE = grid_points(can_flag, n)
-    sh = query_pts.shape
     dev = sp_input["img_all"].device
-    flat = torch.from_numpy(query_pts.reshape([-1, 3])).to(dev).float()
+    query_pts, START, SIZE, RANGE = grid_points(can_flag, n, device=dev)
+    sh = query_pts.shape
+    flat = query_pts.reshape([-1, 3])
     if can_flag:
         net.set_extract_mesh(True)
         t_vertices = sp_input["t_vertices"].reshape(-1, 3)

@@ -106,3 +106,16 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.mpsnerf_abi_version() == 1
     assert ctypes.sizeof(_lib.Frame) == 4 * (3 + 9 + 9 + 3 + 4 * 288 + 72 + 24 + 72 + 8)
+
+
+def test_mesh_grid_points_device_form_matches_numpy_meshgrid():
+    """extract_thuman_mesh.grid_points: the broadcast form used on the device equals the reference's
+    np.stack(np.meshgrid(...)).astype(float32) bit for bit (checked here on the CPU device)."""
+    import numpy as np
+    import torch
+    from mpsnerf_b200 import extract_thuman_mesh as X
+    for can in (False, True):
+        ref, S0, Z0, R0 = X.grid_points(can, 16)
+        got, S1, Z1, R1 = X.grid_points(can, 16, device=torch.device("cpu"))
+        assert ref.dtype == np.float32 and tuple(got.shape) == ref.shape
+        assert np.array_equal(got.numpy(), ref) and np.array_equal(R0, R1) and np.array_equal(S0, S1)
