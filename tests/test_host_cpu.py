@@ -119,3 +119,26 @@ def test_mesh_grid_points_device_form_matches_numpy_meshgrid():
         got, S1, Z1, R1 = X.grid_points(can, 16, device=torch.device("cpu"))
         assert ref.dtype == np.float32 and tuple(got.shape) == ref.shape
         assert np.array_equal(got.numpy(), ref) and np.array_equal(R0, R1) and np.array_equal(S0, S1)
+
+
+def test_hot_input_selection_for_host_dicts():
+    """render() uploads only the dict entries the path reads (run_nerf_batch.HOT_KEYS_*): the selection keeps
+    nested params, drops e.g. the target view's images, and hot_input_bytes counts exactly the kept tensors."""
+    import torch
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    sc = synthetic.make_scene("thuman", seed=0, H=64, W=64)
+    sp = R._upload_hot(sc.sp_input, R.HOT_KEYS_SP, torch.device("cpu"))
+    tp = R._upload_hot(sc.tp_input, R.HOT_KEYS_TP, torch.device("cpu"))
+    assert set(sp) == set(R.HOT_KEYS_SP) and set(tp) == set(R.HOT_KEYS_TP)
+    assert "img_all" not in tp and set(tp["params"]) == set(sc.tp_input["params"])
+    assert torch.equal(sp["img_all"], sc.sp_input["img_all"]) and torch.equal(tp["vertices"], sc.tp_input["vertices"])
+    count = lambda d: sum(v.numel() * v.element_size() if torch.is_tensor(v) else count(v) if isinstance(v, dict) else 0 for v in d.values())
+    assert R.hot_input_bytes(sc.sp_input, sc.tp_input) == count(sp) + count(tp)
+    assert R.hot_input_bytes(sc.sp_input, sc.tp_input) < count(sc.sp_input) + count(sc.tp_input)
+    # every key the engine / frame cache reads is in the selection
+    import inspect
+    from mpsnerf_b200 import engine
+    src = inspect.getsource(engine.RenderEngine._prepare_frame)
+    for key in ("img_all", "R_all", "T_all", "K_all", "t_vertices", "params"):
+        assert f'sp["{key}"]' in src and key in R.HOT_KEYS_SP
+    assert 'tp["vertices"]' in src and "vertices" in R.HOT_KEYS_TP
