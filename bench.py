@@ -5,8 +5,10 @@ A step = one full novel-view render (BASELINE.json configs[1]: canonical_transfo
 3 input views 512x512, 262 144 rays x 64 samples) through the public ``render()`` API.
 ``value`` times it with all inputs resident in HBM; ``e2e`` times the same call with HOST
 (pinned) inputs, H2D copies and the D2H read of the rendered image inside the timed region.
-Multi-GPU: one process per GPU (torchrun), every rank renders its own target view of the same
-scene (weak scaling, no data-path collective); time = max over ranks.
+Multi-GPU: one process per GPU (torchrun).  Default for N > 1 = the north-star split (BASELINE configs[2]): the rays
+of ONE H36M-shaped 1000x1000 target view dealt out to the N GPUs in interleaved row groups, every rank generating
+its own rays on the device (strong scaling, no data-path collective); --mode weak = one target view per GPU.
+Time = max over ranks.
 
 ``--impl reference`` times the reference algorithm's CPU implementation (the oracle port,
 oracle/oracle.py) on a bounded ray sample of the same workload on the host cores.
@@ -74,6 +76,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows)}
 
 
+def workload_config(workload, world, strong):
+    """The ``config`` object of the JSON line: identical in both arms (ours / --impl reference) by construction."""
+    w = WORKLOADS[workload]
+    return {"workload": w[2], "samples_per_ray": 64, "input_views": 3, "image": w[3],
+            "network": "configs/%s (skinning_batch), seeded random weights (synthetic.seeded_state_dict(0, 300))" % w[1],
+            "extras": "full reference contract (raw, pts_mask, smpl_query_pts, smpl_src_pts)",
+            "includes": "per-frame prep + encoder trunk + K1..K6", "l2": "flushed between timed steps (512 MiB fill)",
+            "parallelism": (f"ONE target view dealt out to {world} GPUs in interleaved groups of 2 image rows, rays generated "
+                            f"on each GPU from the camera; no data-path collective" if strong
+                            else f"one target view per GPU x{world}")}
+
+
+def resolve_mode(a):
+    """N = 1: BASELINE configs[1] (thuman 512x512 frame).  N > 1: BASELINE configs[2] -- ONE H36M-shaped 1000x1000
+    frame split over the N GPUs (strong scaling) -- unless --workload / --mode say otherwise."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = a.workload or ("thuman" if world == 1 else "h36m")
+    strong = (world > 1) if a.mode == "auto" else (a.mode == "strong")
+    return world, workload, strong
+
+
 def build_scene_and_net(precision, target_view, workload="thuman"):
     from mpsnerf_b200 import synthetic
     from mpsnerf_b200.lib import skinnning_batch as SB
@@ -90,6 +113,7 @@ def build_scene_and_net(precision, target_view, workload="thuman"):
         scene.rays_o, scene.rays_d = ro, rd
         scene.near, scene.far = np.zeros(len(ro), np.float32), np.ones(len(ro), np.float32)
         scene.near[hit], scene.far[hit] = n, f
+        scene.target = target_view % 24
     SB.set_default_smpl_models(scene.smpl)
     args = config_parser().parse_args(["--config", os.path.join(ROOT, "configs", cfg_file),
                                        "--N_samples", "64", "--precision", precision])
@@ -103,8 +127,10 @@ def build_scene_and_net(precision, target_view, workload="thuman"):
 def run_ours(a):
     from mpsnerf_b200 import _lib, synthetic
     from mpsnerf_b200 import run_nerf_batch as R
+    from mpsnerf_b200.lib.if_nerf_data_utils import gen_rays8
+    from mpsnerf_b200.parallel import interleaved_rows
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    world, workload, strong = resolve_mode(a)
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -124,27 +150,16 @@ def run_ours(a):
             os.close(saved)
     dev = torch.device("cuda", local)
     _lib.check(_lib.load().mpsnerf_check_device(local), "check_device")
-    strong = a.workload != "thuman"
-    scene, net, args = build_scene_and_net(a.precision, None if strong else 1 + rank, a.workload)
+    scene, net, args = build_scene_and_net(a.precision, None if (strong or world == 1) else 1 + rank, workload)
     handle = R.NetworkHandle(net).to(dev).eval()
-    rays_h, near_h, far_h = synthetic.rays_tensor(scene, None)
-    n_total = rays_h.shape[2]
-    if strong:                               # this rank's contiguous block of the one frame
-        # Balance by measured work, not by ray count: one untimed profiling render of the whole frame
-        # gives the active samples per ray; a ray costs ~0.6 active-point equivalents on its own (K1 + K6).
-        from mpsnerf_b200.parallel import balanced_ray_block
-        if world > 1:
-            dd = lambda d: {k: (v.to(dev) if torch.is_tensor(v) else dd(v) if isinstance(v, dict) else v) for k, v in d.items()}
-            ex = R.render(rays=rays_h.to(dev), near=near_h.to(dev), far=far_h.to(dev), sp_input=dd(scene.sp_input),
-                          tp_input=dd(scene.tp_input), network_fn=handle, N_samples=64, perturb=False, use_viewdirs=True)[3]
-            weights = ex["pts_mask"][0, ..., 0].sum(-1).double().cpu() + 0.6
-            del ex
-            torch.cuda.empty_cache()
-        else:
-            weights = scene.mask_at_box
-        s0, s1 = balanced_ray_block(weights, rank, world)
-        rays_h, near_h, far_h = rays_h[:, :, s0:s1].contiguous(), near_h[:, s0:s1].contiguous(), far_h[:, s0:s1].contiguous()
-    n_rays = rays_h.shape[2]
+    H, W = scene.H, scene.W
+    n_total = H * W
+    Kc, Rc, Tc = scene.cams[scene.target]
+    # this rank's share of the target view: all of it, or interleaved groups of two image rows of the ONE frame
+    rows = interleaved_rows(H, rank, world, 2).to(dev) if (strong and world > 1) else None
+    camera = dict(K=Kc, R=Rc, T=Tc, bounds=scene.bounds, H=H, W=W, rows=rows)
+    rays8, box = gen_rays8(H, W, Kc, Rc, Tc, scene.bounds, device=dev, rows=rows)
+    n_rays = rays8.shape[0]
 
     def pin(d):
         return {k: (v.pin_memory() if torch.is_tensor(v) else pin(v) if isinstance(v, dict) else v) for k, v in d.items()}
@@ -154,41 +169,49 @@ def run_ours(a):
                 for k, v in d.items()}
 
     sp_h, tp_h = pin(scene.sp_input), pin(scene.tp_input)
-    rays_h, near_h, far_h = rays_h.pin_memory(), near_h.pin_memory(), far_h.pin_memory()
     sp_d, tp_d = to_dev(sp_h), to_dev(tp_h)
-    rays_d, near_d, far_d = rays_h.to(dev), near_h.to(dev), far_h.to(dev)
+    # resident inputs in the reference's own layout: rays (1,2,N,3), near / far (1,N,1)
+    rays_d = torch.stack([rays8[:, 0:3], rays8[:, 3:6]])[None].contiguous()
+    near_d, far_d = rays8[None, :, 6:7].contiguous(), rays8[None, :, 7:8].contiguous()
+    rays_h, near_h, far_h = rays_d.cpu().pin_memory(), near_d.cpu().pin_memory(), far_d.cpu().pin_memory()
     kw = dict(network_fn=handle, N_samples=64, perturb=False, use_viewdirs=True, chunk=args.chunk)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     out_h = [torch.empty(1, n_rays, 3).pin_memory(), torch.empty(1, n_rays).pin_memory(), torch.empty(1, n_rays).pin_memory()]
-
-    def tensor_bytes(d):
-        return sum(v.numel() * v.element_size() if torch.is_tensor(v) else tensor_bytes(v) if isinstance(v, dict) else 0
-                   for v in d.values())
-
-    h2d = R.hot_input_bytes(sp_h, tp_h) + sum(t.numel() * 4 for t in (rays_h, near_h, far_h))
+    hot = R.hot_input_bytes(sp_h, tp_h)
+    cam_bytes = (9 + 9 + 3 + 6) * 8 + (0 if rows is None else rows.numel() * 4)
     d2h = sum(t.numel() * 4 for t in out_h)
 
     def step_resident():
         return R.render(rays=rays_d, near=near_d, far=far_d, sp_input=sp_d, tp_input=tp_d, **kw)
 
-    def step_e2e():
-        # everything starts in pinned host memory: render() uploads the entries of sp / tp that the path reads
-        # (R.HOT_KEYS_*; not, e.g., the target view's own images) and, on a copy stream under the frame
-        # preparation, rays / near / far
-        rgb, disp, acc, _ = R.render(rays=rays_h, near=near_h, far=far_h, sp_input=sp_h, tp_input=tp_h, **kw)
+    def read_back(rgb, disp, acc):
         out_h[0].copy_(rgb, non_blocking=True)
         out_h[1].copy_(disp, non_blocking=True)
         out_h[2].copy_(acc, non_blocking=True)
+
+    def step_e2e():
+        # everything starts on the host: pinned dicts (render() uploads the entries the path reads, R.HOT_KEYS_*) and
+        # the target camera; the rays are generated on the device from it (csrc/raygen.cu), the image is read back
+        rgb, disp, acc, _ = R.render(camera=camera, sp_input=sp_h, tp_input=tp_h, **kw)
+        read_back(rgb, disp, acc)
+
+    def step_e2e_host_rays():
+        # round-1 form of the same call: rays / near / far built on the host and uploaded (32 B per ray)
+        rgb, disp, acc, _ = R.render(rays=rays_h, near=near_h, far=far_h, sp_input=sp_h, tp_input=tp_h, **kw)
+        read_back(rgb, disp, acc)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, collective=True):
         for _ in range(warmup):
             fn()
-        barrier()
+        if collective:
+            barrier()
+        else:
+            torch.cuda.synchronize()
         ms = []
         for _ in range(steps):
             flush.fill_(1)
@@ -198,6 +221,8 @@ def run_ours(a):
             e1.record()
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
+        if not collective:
+            return sum(ms), ms
         barrier()
         t = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
         if world > 1:
@@ -211,7 +236,8 @@ def run_ours(a):
     total_ms, per = timed(step_resident, a.steps, warm)
     launches = (_lib.LAUNCHES - l0) * a.steps // (a.steps + warm)
     clocks = sampler.stop()
-    e2e_ms, _ = timed(step_e2e, a.steps, 1)
+    e2e_ms, _ = timed(step_e2e, a.steps, 2)
+    e2e_host_ms, _ = timed(step_e2e_host_rays, max(a.steps // 2, 2), 1)
 
     # per-stage device times of the same step (separate passes, CUDA events on the launch stream)
     eng = net.engine()
@@ -223,27 +249,49 @@ def run_ours(a):
     stage_ms = {k: float(sum(s.elapsed_time(e) for s, e in v)) / 3 for k, v in eng.timers.items()}   # per step
     n_active = eng.last_active
     eng.timers = None
+
+    # N > 1, strong: the same frame on ONE GPU (rank 0, the others wait), in the same run on the same box -- the
+    # denominator a reader needs next to the N-GPU value (the driver's own N = 1 line is another workload)
+    single = None
+    if strong and world > 1:
+        if rank == 0:
+            r8, _ = gen_rays8(H, W, Kc, Rc, Tc, scene.bounds, device=dev)
+            full = dict(rays=torch.stack([r8[:, 0:3], r8[:, 3:6]])[None].contiguous(), near=r8[None, :, 6:7].contiguous(),
+                        far=r8[None, :, 7:8].contiguous())
+            ms1, _ = timed(lambda: R.render(sp_input=sp_d, tp_input=tp_d, **full, **kw), max(a.steps // 2, 3), 2, collective=False)
+            single = {"ms_per_step": ms1 / max(a.steps // 2, 3), "rays_per_s": n_total * max(a.steps // 2, 3) / (ms1 * 1e-3),
+                      "what": "the whole frame on rank 0 alone, same run, resident inputs"}
+            del full, r8
+        barrier()
+    # load balance of the split: active points per rank
+    act = torch.tensor([float(n_active)], device=dev, dtype=torch.float64)
+    acts = [act.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(acts, act)
+    acts = [int(x.item()) for x in acts]
+
     pk = peaks()
+    FLOP_T, FLOP_M = FLOP_PER_ACTIVE_POINT - 1353728, 1353728       # algorithmic minimum per active point, each kernel
     if "dense" not in stage_ms and "dense_t" in stage_ms:
         stage_ms["dense"] = stage_ms["dense_t"] + stage_ms["dense_m"]
     dense_ms = stage_ms.get("dense", float("nan"))
-    ach = n_active * FLOP_PER_ACTIVE_POINT / (dense_ms * 1e-3) / 1e12
-    # DRAM bytes of the dense stage (T + M kernels) per step from the committed `ncu --set full` capture
-    traffic = None
+    # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels (NOT measured in this run)
+    traffic, tsrc = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dense_" + a.precision)
+    if os.path.exists(tpath) and a.precision == "bf16" and workload == "thuman" and world == 1:
+        tj = json.load(open(tpath))
+        traffic, tsrc = tj.get("xformer_bf16"), "profiles/ncu_traffic.json: " + str(tj.get("xformer_bf16_source"))
     # HBM-side figures of the other kernels: algorithmic bytes / CUDA-event time
     n_pts, V = n_rays * 64, 3
+    Hf, Wf = (H // 2 - 1) // 2 + 1, (W // 2 - 1) // 2 + 1
     alg_bytes = {"k1_sample_knn": n_pts * 44 + n_rays * 32, "k3_deform": n_active * (20 + 48),
                  # K4: compulsory HBM bytes = tokens written + uv read + one pass over the latent / image planes;
                  # its 4 taps x 128 channels per (point, view) are L2 hits (reported as l2_bytes below)
-                 "k4_gather": n_active * V * (8 + 160 * (2 if a.precision == "bf16" else 4)) + V * (128 * 128 * 128 + 512 * 512 * 4) * 4,
+                 "k4_gather": n_active * V * (8 + 160 * (2 if a.precision == "bf16" else 4)) + V * (Hf * Wf * 128 + H * W * 4) * 4,
                  "k6_composite": n_rays * (64 * 16 + 52)}
     kernels = {k: {"bytes": b, "ms": stage_ms.get(k), "achieved_gbs": b / (stage_ms[k] * 1e-3) / 1e9,
                    "frac_of_hbm_peak": b / (stage_ms[k] * 1e-3) / 1e9 / pk["hbm"]} for k, b in alg_bytes.items() if stage_ms.get(k)}
-    # the two fused tensor-core kernels on their own (algorithmic minimum FLOP per active point each)
-    for k, fl in (("dense_t", FLOP_PER_ACTIVE_POINT - 1353728), ("dense_m", 1353728)):
+    for k, fl in (("dense_t", FLOP_T), ("dense_m", FLOP_M)):
         if stage_ms.get(k):
             t = n_active * fl / (stage_ms[k] * 1e-3) / 1e12
             kernels[k] = {"flop_per_active_point": fl, "ms": stage_ms[k], "achieved_tflops": t,
@@ -251,51 +299,75 @@ def run_ours(a):
     if "k4_gather" in kernels:
         kernels["k4_gather"]["l2_bytes"] = n_active * V * (4 * 128 + 16) * 4
         kernels["k4_gather"]["l2_gbs"] = kernels["k4_gather"]["l2_bytes"] / (stage_ms["k4_gather"] * 1e-3) / 1e9
-    roofline = {"bound": "tensor", "kernel": "dense_" + a.precision, "achieved": ach, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["src"] + " sustained bf16",
-                "kernel_ms": dense_ms, "active_points": n_active, "flop_per_active_point": FLOP_PER_ACTIVE_POINT,
+    if a.precision == "bf16" and stage_ms.get("dense_t"):
+        # the dominant kernel of the step: the cross-view transformer (xformer_tc_kernel)
+        kname, kms, kflop = "xformer_tc_kernel (dense_t)", stage_ms["dense_t"], FLOP_T
+    else:
+        kname, kms, kflop = "dense_" + a.precision, dense_ms, FLOP_PER_ACTIVE_POINT
+    ach = n_active * kflop / (kms * 1e-3) / 1e12
+    stage_ach = n_active * FLOP_PER_ACTIVE_POINT / (dense_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_sustained"], "traffic": traffic, "traffic_source": tsrc,
+                "peak_source": pk["src"] + " sustained bf16", "kernel_ms": kms, "active_points": n_active,
+                "flop_per_active_point": kflop,
+                "stage": {"what": "T + M (transformer + MLP), the dense stage", "ms": dense_ms, "achieved": stage_ach,
+                          "frac": stage_ach / pk["bf16_sustained"], "flop_per_active_point": FLOP_PER_ACTIVE_POINT},
                 "stage_ms": stage_ms, "kernels": kernels, "hbm_peak_gbs": pk["hbm"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = cpu_baseline(budget_s=20.0)
+    cpu = cpu_baseline(budget_s=20.0, workload=workload)
     rays_per_step = n_total if strong else n_rays * world
     res = {
         "metric": "rays/sec (render fwd)", "value": rays_per_step * a.steps / (total_ms * 1e-3), "unit": "rays/s",
         "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-        "config": {"workload": WORKLOADS[a.workload][2], "rays_per_gpu_per_step": n_rays, "samples_per_ray": 64, "input_views": 3,
-                   "image": WORKLOADS[a.workload][3], "network": "configs/%s (skinning_batch), seeded random weights" % WORKLOADS[a.workload][1],
-                   "extras": "full reference contract (raw, pts_mask, smpl_query_pts, smpl_src_pts)",
-                   "includes": "per-frame prep + encoder trunk + K1..K6", "l2": "flushed between timed steps (512 MiB fill)",
-                   "parallelism": (f"rays: {world} contiguous blocks of one target view, balanced by active samples per ray "
-                                   f"(one untimed profiling render)" if strong
-                                   else f"rays: one target view per GPU x{world}")},
-        "e2e": {"value": rays_per_step * a.steps / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
+        "config": workload_config(workload, world, strong),
+        "e2e": {"value": rays_per_step * a.steps / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": hot + cam_bytes,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
+                "what": "render(camera=...) with pinned host dicts: uploads + device ray generation + image read-back",
+                "host_rays_variant": {"ms_per_step": e2e_host_ms / max(a.steps // 2, 2),
+                                      "h2d_bytes_per_step": hot + sum(t.numel() * 4 for t in (rays_h, near_h, far_h)),
+                                      "what": "rays / near / far built on the host and uploaded (round-1 e2e)"}},
+        "rays_per_gpu_per_step": n_rays, "active_points_per_gpu": acts,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
+    if single is not None:
+        res["single_gpu_same_workload"] = single
     print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(budget_s=20.0, n_rays=None, steps=1, warmup=0):
-    """Time the oracle port (reference algorithm on CPU) on in-box rays of the same scene."""
+def cpu_baseline(budget_s=20.0, n_rays=None, steps=1, warmup=0, workload="thuman"):
+    """Time the reference algorithm on the host cores on in-box rays of the bench scene (BASELINE config 1 shape):
+    the UNMODIFIED reference under import shims when its tree is present ($MPSNERF_REF, /root/reference,
+    baseline/_ref; kind "reference"), else the oracle port (kind "port": the GPU box never has the tree)."""
     from mpsnerf_b200 import synthetic
     from oracle import oracle as O
+    from oracle import run_reference as RR
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    scene = synthetic.make_scene("thuman", seed=0)
+    scene = synthetic.make_scene(WORKLOADS[workload][0], seed=0)
     sd = synthetic.seeded_state_dict(0, 300.0)
+    kind = "port"
+    if RR.find_reference() is not None and os.environ.get("MPSNERF_CPU_ARM", "auto") != "port":
+        try:
+            R, wrapped = RR.load(scene, sd)
+            kind = "reference"
+        except Exception as e:          # a tree that does not import here: say so and time the port
+            sys.stderr.write(f"bench: reference tree found but not runnable ({type(e).__name__}: {e}); timing the port\n")
     smpl = O.smpl_tensors(scene.smpl)
 
     def run(n):
         ids = synthetic.inbox_ray_subset(scene, n)
         t0 = time.perf_counter()
-        O.render(smpl, sd, scene.sp_input, scene.tp_input, scene.rays_o[ids], scene.rays_d[ids], scene.near[ids],
-                 scene.far[ids], S=64)
+        if kind == "reference":
+            RR.render(R, wrapped, scene, ids, S=64)
+        else:
+            O.render(smpl, sd, scene.sp_input, scene.tp_input, scene.rays_o[ids], scene.rays_d[ids], scene.near[ids],
+                     scene.far[ids], S=64)
         return time.perf_counter() - t0
 
     if n_rays is None:
@@ -304,20 +376,23 @@ def cpu_baseline(budget_s=20.0, n_rays=None, steps=1, warmup=0):
     for _ in range(warmup):
         run(n_rays)
     ts = [run(n_rays) for _ in range(steps)]
-    return {"value": n_rays * len(ts) / sum(ts), "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{n_rays} in-box rays x 64 samples of the same scene, {len(ts)} pass(es), torch CPU fp32, "
-                      f"{cores} threads, encoder included once per pass", "seconds": sum(ts)}
+    what = "the unmodified reference (oracle/ref_shims.py)" if kind == "reference" else "oracle port (oracle/oracle.py)"
+    return {"value": n_rays * len(ts) / sum(ts), "unit": "rays/s", "cores": cores, "kind": kind,
+            "sample": f"{n_rays} in-box rays x 64 samples of the same scene and weights, {len(ts)} pass(es), {what}, "
+                      f"torch CPU fp32, {cores} threads, encoder included once per pass", "seconds": sum(ts)}
 
 
 def run_reference(a):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cpu = cpu_baseline(budget_s=150.0, steps=a.steps, warmup=a.warmup)
+    world, workload, strong = resolve_mode(a)
+    cpu = cpu_baseline(budget_s=150.0, steps=a.steps, warmup=a.warmup, workload=workload)
     print(json.dumps({
         "impl": "reference", "metric": "rays/sec (render fwd)", "value": cpu["value"], "unit": "rays/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * cpu["seconds"] / a.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "each step = a bounded ray sample of the workload on host cores"},
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(workload, world, strong),
+        "note": "each step = a bounded ray sample of the workload on the host cores (cpu_baseline.sample)",
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -329,7 +404,10 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MPSNERF_PRECISION", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--workload", default="thuman", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: thuman (BASELINE configs[1]) on 1 GPU, h36m (configs[2]) on several")
+    ap.add_argument("--mode", default="auto", choices=["auto", "strong", "weak"],
+                    help="N > 1: strong = ONE frame split over the GPUs (default), weak = one target view per GPU")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -83,6 +83,20 @@ int mpsnerf_frame_prepare(const float* poses_tp, const float* shapes_tp, const f
                           const float* shapedirs, const float* J_regressor, const int32_t* parents,
                           int n_verts, mpsnerf_frame* out, void* stream);
 
+/* The two halves of mpsnerf_frame_prepare as separate launches (calling both, in any order or on different streams,
+ * equals the call above; they write disjoint fields of *out):
+ *  - header: the fields that are copies of the inputs -- Th_tp, R_tp (lib/skinnning_batch.py:345-347), Th_sp, the 3x3
+ *    inverse of R_sp (:297), cameras, sizes.  A few microseconds, and all that K1 needs of the frame.
+ *  - transforms: the four LBS transform sets (lib/run_nerf_helpers.py:174-254, lib/skinnning_batch.py:193-201),
+ *    evaluated in float64 and rounded to fp32 once.  Needed from K3 on. */
+int mpsnerf_frame_header(const float* R_tp, const float* Th_tp, const float* R_sp, const float* Th_sp,
+                         const float* cam_R, const float* cam_T, const float* cam_K, int n_views,
+                         int img_w, int img_h, int feat_w, int feat_h, mpsnerf_frame* out, void* stream);
+int mpsnerf_frame_transforms(const float* poses_tp, const float* shapes_tp, const float* poses_sp,
+                             const float* shapes_sp, const float* v_template, const float* shapedirs,
+                             const float* J_regressor, const int32_t* parents, int n_verts,
+                             mpsnerf_frame* out, void* stream);
+
 /* ---- nearest-vertex acceleration grid -------------------------------------------------
  * Replaces the brute-force pytorch3d knn_points calls (lib/skinnning_batch.py:214,256,357)
  * with an exact uniform-grid search.  If Th/R are non-null the vertices are first taken to
@@ -144,6 +158,13 @@ int mpsnerf_deform_project(const int32_t* act_pid, const int32_t* act_idx2, cons
  * (mask_at_box may be NULL). */
 int mpsnerf_gen_rays(const double* K, const double* R, const double* T, const double* bounds, int32_t H,
                      int32_t W, float* rays8, uint8_t* mask_at_box, void* stream);
+
+/* Same for a subset of the image rows: rows (n_rows) is a DEVICE list of row indices in [0, H); output ray
+ * p = pixel (rows[p / W], p % W), so rays8 holds n_rows * W rays.  This is how one target view is dealt out to
+ * several GPUs (each rank generates only its own rows; no ray upload, no scatter). */
+int mpsnerf_gen_rays_rows(const double* K, const double* R, const double* T, const double* bounds, int32_t H,
+                          int32_t W, const int32_t* rows, int32_t n_rows, float* rays8, uint8_t* mask_at_box,
+                          void* stream);
 
 /* ---- K4: multiview bilinear feature + RGB lookup, RGB positional code -> tokens --------
  * Replaces SpatialEncoder.index / grid_sample (lib/encoder.py:12-62, 225-253) and the RGB

@@ -1,7 +1,8 @@
 """ctypes binding of libmpsnerf_b200.so (the C ABI declared in include/mpsnerf.h).
 
-There is no CPU fallback: if the library is missing it is built once with nvcc
-(``build.py``); if that fails, or a call returns an error code, a RuntimeError is raised.
+There is no CPU fallback: if the library is missing or was built from other sources than the
+ones in the tree (source hash, ``build.py``) it is rebuilt with nvcc; if that fails, or a call
+returns an error code, a RuntimeError is raised.
 """
 import ctypes
 import os
@@ -12,6 +13,7 @@ c_void_p, c_int, c_int32, c_int64, c_size_t, c_float = (ctypes.c_void_p, ctypes.
                                                        ctypes.c_int64, ctypes.c_size_t, ctypes.c_float)
 
 MAX_VIEWS = 8
+MAX_VIEWS_TC = 4        # tensor-core (bf16) path: a point's V tokens must fit one 128-row tile several times over
 NUM_JOINTS = 24
 TOKEN_DIM = 155
 TOKEN_LD = 160
@@ -34,6 +36,8 @@ SIGNATURES = {
     "mpsnerf_abi_version": (c_int, []),
     "mpsnerf_check_device": (c_int, [c_int]),
     "mpsnerf_frame_prepare": (c_int, [c_void_p] * 11 + [c_int] * 5 + [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
+    "mpsnerf_frame_header": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p, c_void_p]),
+    "mpsnerf_frame_transforms": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
     "mpsnerf_grid_bytes": (c_size_t, [c_int]),
     "mpsnerf_grid_build": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
     "mpsnerf_knn1": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -55,6 +59,8 @@ SIGNATURES = {
     "mpsnerf_mlp_bf16_dc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
     "mpsnerf_gen_rays": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_gen_rays_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p,
+                                      c_void_p, c_void_p]),
     "mpsnerf_gather_tokens_f16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_dense_fp32_workspace": (c_size_t, [c_int64, c_int]),
     "mpsnerf_dense_fp32": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
@@ -86,8 +92,9 @@ def load():
     """Load (building first if needed) and type every exported symbol."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_build.LIB):
-            _build.build()
+        # always go through build(): a cheap source-hash check that rebuilds a stale or missing library (under a
+        # file lock, atomically replaced) -- a leftover .so from an older checkout is never loaded silently
+        _build.build()
         lib = ctypes.CDLL(_build.LIB)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)      # AttributeError if the .so lacks a declared symbol

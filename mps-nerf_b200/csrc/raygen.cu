@@ -20,10 +20,13 @@ struct RayCam {
 };
 
 __global__ void __launch_bounds__(256)
-raygen_kernel(const RayCam cam, int H, int W, float* __restrict__ rays8, uint8_t* __restrict__ mask_at_box) {
-  const int64_t n = (int64_t)H * W;
+raygen_kernel(const RayCam cam, int H, int W, const int32_t* __restrict__ rows, int n_rows, float* __restrict__ rays8,
+              uint8_t* __restrict__ mask_at_box) {
+  // rows == nullptr: the whole H x W view; else only the listed image rows, packed in list order (ray p = pixel
+  // (rows[p / W], p % W)): how one frame is dealt out to several GPUs
+  const int64_t n = (int64_t)(rows ? n_rows : H) * W;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-    const double i = (double)(p % W), j = (double)(p / W);
+    const double i = (double)(p % W), j = (double)(rows ? rows[p / W] : (int)(p / W));
     // pixel_camera = [i, j, 1] @ inv(K).T ; pixel_world = (pixel_camera - T) @ R   (ref :19-20)
     double pc[3], d[3];
 #pragma unroll
@@ -75,10 +78,10 @@ raygen_kernel(const RayCam cam, int H, int W, float* __restrict__ rays8, uint8_t
 }  // namespace mps
 
 // K, R: 3x3 row-major, T: 3, bounds: (2,3) min/max -- HOST pointers (a handful of doubles per view).
-extern "C" int mpsnerf_gen_rays(const double* K, const double* R, const double* T, const double* bounds, int32_t H,
-                                int32_t W, float* rays8, uint8_t* mask_at_box, void* stream) {
+static int gen_rays_impl(const double* K, const double* R, const double* T, const double* bounds, int32_t H, int32_t W,
+                         const int32_t* rows, int32_t n_rows, float* rays8, uint8_t* mask_at_box, void* stream) {
   MPS_REQUIRE(K && R && T && bounds && rays8);
-  MPS_REQUIRE(H >= 1 && W >= 1);
+  MPS_REQUIRE(H >= 1 && W >= 1 && n_rows >= 0);
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(rays8) & 15) == 0);
   mps::RayCam cam;
   // inverse of K (general 3x3, adjugate / determinant)
@@ -95,10 +98,24 @@ extern "C" int mpsnerf_gen_rays(const double* K, const double* R, const double* 
     cam.bmin[k] = bounds[k] - 0.01;                                      // ref :57
     cam.bmax[k] = bounds[3 + k] + 0.01;
   }
-  const int64_t n = (int64_t)H * W;
+  const int64_t n = (int64_t)(rows ? n_rows : H) * W;
+  if (n == 0) return MPSNERF_OK;
   int64_t blocks = (n + 255) / 256;
   if (blocks > mps::kNumSMs * 16) blocks = mps::kNumSMs * 16;
-  mps::raygen_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(cam, H, W, rays8, mask_at_box);
+  mps::raygen_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(cam, H, W, rows, n_rows, rays8, mask_at_box);
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
+}
+
+extern "C" int mpsnerf_gen_rays(const double* K, const double* R, const double* T, const double* bounds, int32_t H,
+                                int32_t W, float* rays8, uint8_t* mask_at_box, void* stream) {
+  return gen_rays_impl(K, R, T, bounds, H, W, nullptr, 0, rays8, mask_at_box, stream);
+}
+
+extern "C" int mpsnerf_gen_rays_rows(const double* K, const double* R, const double* T, const double* bounds, int32_t H,
+                                     int32_t W, const int32_t* rows, int32_t n_rows, float* rays8, uint8_t* mask_at_box,
+                                     void* stream) {
+  MPS_REQUIRE(rows != nullptr || n_rows == 0);
+  if (n_rows == 0) return MPSNERF_OK;
+  return gen_rays_impl(K, R, T, bounds, H, W, rows, n_rows, rays8, mask_at_box, stream);
 }

@@ -1,13 +1,18 @@
 // K1: stratified sampling + world->SMPL + human-region mask + nearest posed vertex + compaction.
 //
-// One thread per sample point, 256 points per block iteration, three phases:
-//   1. every thread generates its point, moves it to SMPL space (pinned fp32) and tests one
-//      bit of the dilated occupancy bitmap; survivors are compacted into a candidate list;
-//   2. the candidate list is processed densely (one thread per candidate) with the exact
-//      27-cell search -- this keeps warps full although only ~15% of the points of a frame
-//      are candidates;
-//   3. every thread writes the per-point outputs of its own point and the active points are
-//      compacted into the global active list (one atomicAdd per block).
+// Two kernels with identical results:
+//  * sample_knn_warp_kernel (default): warp-autonomous.  A warp owns 32 consecutive sample points per iteration
+//    and never meets a block barrier: every lane generates its point, moves it to SMPL space (pinned fp32) and
+//    tests one bit of the dilated occupancy bitmap; the survivors ("candidates", ~15 % of a frame) are searched
+//    four at a time, eight lanes per candidate -- a lane scans one x-run of the 27-cell neighbourhood (lane 0 of
+//    a group two), the (d2, index) minimum is reduced with three shuffle steps -- and the active points are
+//    compacted with one ballot and one atomicAdd per warp.  Per-point outputs are written straight from
+//    registers (raw / mask) or through a 384-byte per-warp staging row (smpl_query, so that the stores are
+//    128-bit and coalesced).
+//  * sample_knn_kernel (MPSNERF_K1=block): the round-1 block-synchronous form -- 256 points per block
+//    iteration, candidates compacted across the block, six barriers per iteration.  Kept for A/B timing.
+#include <stdlib.h>
+
 #include "grid.cuh"
 
 namespace mps {
@@ -131,6 +136,143 @@ sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const
   }
 }
 
+// ---- warp-autonomous form ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kK1Threads)
+sample_knn_warp_kernel(const float* __restrict__ rays, int64_t n_points, int S, const float* __restrict__ t_vals,
+                       const float* __restrict__ u, const float* __restrict__ points,
+                       const mpsnerf_frame* __restrict__ frame, const char* __restrict__ grid_buf,
+                       float* __restrict__ raw, float* __restrict__ pts_mask, float* __restrict__ smpl_query,
+                       float* __restrict__ smpl_src, int32_t* __restrict__ act_pid, int32_t* __restrict__ act_idx2,
+                       float* __restrict__ act_q, int32_t* __restrict__ act_count) {
+  const GridView g = grid_view(grid_buf);
+  __shared__ GridHdr s_hdr;
+  __shared__ float s_fr[12];                                     // Th(3) R(9)
+  __shared__ __align__(16) float s_stage[kK1Threads / 32][96];   // one smpl_query row block per warp
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_hdr = *g.hdr;
+  if (tid < 3) s_fr[tid] = frame->Th_tp[tid];
+  if (tid >= 3 && tid < 12) s_fr[tid] = frame->R_tp[tid - 3];
+  __syncthreads();
+  const GridHdr h = s_hdr;
+  const float INF = __int_as_float(0x7f800000);
+  const int sub = lane & 7, grp = lane >> 3;
+  float* stage = s_stage[wid];
+  const int64_t nchunks = (n_points + 31) >> 5;
+  constexpr int kWarps = kK1Threads / 32;
+
+  for (int64_t c = (int64_t)blockIdx.x * kWarps + wid; c < nchunks; c += (int64_t)gridDim.x * kWarps) {
+    const int64_t base = c << 5, pid = base + lane;
+    const bool valid = pid < n_points;
+    // ---- every lane: its point in SMPL space, one bitmap test
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int cx = 0, cy = 0, cz = 0;
+    bool cand = false;
+    if (valid) {
+      float px, py, pz;
+      if (points != nullptr) {
+        px = points[3 * pid]; py = points[3 * pid + 1]; pz = points[3 * pid + 2];
+      } else {
+        // P < 2^31 (checked by the host wrapper): 32-bit division instead of the ~100-instruction 64-bit one
+        const uint32_t r = (uint32_t)pid / (uint32_t)S;
+        const int s = (int)((uint32_t)pid - r * (uint32_t)S);
+        const float4 ra = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r);       // o.xyz, d.x
+        const float4 rb = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r + 1);   // d.yz, near, far
+        const float z = sample_z(rb.z, rb.w, t_vals, s, S, u ? u + (size_t)r * S : nullptr);
+        px = padd(ra.x, pmul(ra.w, z));     // run_nerf_batch.py:424
+        py = padd(ra.y, pmul(rb.x, z));
+        pz = padd(ra.z, pmul(rb.y, z));
+      }
+      const float d0 = psub(px, s_fr[0]), d1 = psub(py, s_fr[1]), d2 = psub(pz, s_fr[2]);
+      qx = padd(padd(pmul(d0, s_fr[3]), pmul(d1, s_fr[6])), pmul(d2, s_fr[9]));   // (p-Th)@R, :347
+      qy = padd(padd(pmul(d0, s_fr[4]), pmul(d1, s_fr[7])), pmul(d2, s_fr[10]));
+      qz = padd(padd(pmul(d0, s_fr[5]), pmul(d1, s_fr[8])), pmul(d2, s_fr[11]));
+      cx = cell_coord(qx, h.ox, h.inv_cell); cy = cell_coord(qy, h.oy, h.inv_cell); cz = cell_coord(qz, h.oz, h.inv_cell);
+      cand = grid_maybe_near(h, g.occ, cx, cy, cz);
+    }
+    // ---- candidates, four per pass: lanes [8 k, 8 k + 8) search the k-th remaining candidate
+    float bd2 = INF;
+    int bidx = 0x7fffffff;
+    unsigned cm = __ballot_sync(0xffffffffu, cand);
+    while (cm) {
+      const int b0 = __ffs(cm) - 1;
+      const unsigned m1 = cm & (cm - 1);
+      const int b1 = m1 ? __ffs(m1) - 1 : -1;
+      const unsigned m2 = m1 & (m1 - 1);
+      const int b2 = m2 ? __ffs(m2) - 1 : -1;
+      const unsigned m3 = m2 & (m2 - 1);
+      const int b3 = m3 ? __ffs(m3) - 1 : -1;
+      cm = m3 & (m3 - 1);
+      const int src = grp == 0 ? b0 : grp == 1 ? b1 : grp == 2 ? b2 : b3;
+      const int sl = src < 0 ? 0 : src;
+      const float sx = __shfl_sync(0xffffffffu, qx, sl), sy = __shfl_sync(0xffffffffu, qy, sl), sz = __shfl_sync(0xffffffffu, qz, sl);
+      const int ccx = __shfl_sync(0xffffffffu, cx, sl), ccy = __shfl_sync(0xffffffffu, cy, sl), ccz = __shfl_sync(0xffffffffu, cz, sl);
+      float d = INF;
+      int id = 0x7fffffff;
+      const int x0 = max(ccx - 1, 0), x1 = min(ccx + 1, h.nx - 1);
+      if (src >= 0 && x0 <= x1) {
+#pragma unroll 1
+        for (int rr = sub; rr < 9; rr += 8) {          // x-run rr = (dy, dz); lane 0 of the group also takes run 8
+          const int y = ccy + (rr % 3) - 1, z = ccz + (rr / 3) - 1;
+          if ((unsigned)y >= (unsigned)h.ny || (unsigned)z >= (unsigned)h.nz) continue;
+          const int row = (z * h.ny + y) * h.nx;
+          const int b = __ldg(&g.cell_start[row + x0]);
+          const int e = __ldg(&g.cell_start[row + x1 + 1]);
+          for (int i = b; i < e; ++i) {
+            const float4 v = __ldg(&g.sorted[i]);
+            nn_update(dist2_pinned(sx, sy, sz, v.x, v.y, v.z), __float_as_int(v.w), d, id);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {                // (d2, index) minimum over the group's eight lanes
+        const float od = __shfl_xor_sync(0xffffffffu, d, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+        nn_update(od, oi, d, id);
+      }
+      // hand each group's result to the lane that owns the candidate
+      const float r0 = __shfl_sync(0xffffffffu, d, 0), r1 = __shfl_sync(0xffffffffu, d, 8), r2 = __shfl_sync(0xffffffffu, d, 16),
+                  r3 = __shfl_sync(0xffffffffu, d, 24);
+      const int i0 = __shfl_sync(0xffffffffu, id, 0), i1 = __shfl_sync(0xffffffffu, id, 8), i2 = __shfl_sync(0xffffffffu, id, 16),
+                i3 = __shfl_sync(0xffffffffu, id, 24);
+      if (lane == b0) { bd2 = r0; bidx = i0; }
+      if (lane == b1) { bd2 = r1; bidx = i1; }
+      if (lane == b2) { bd2 = r2; bidx = i2; }
+      if (lane == b3) { bd2 = r3; bidx = i3; }
+    }
+    // ---- outputs and compaction
+    const bool active = valid && (bd2 < kMaskThresh);     // lib/skinnning_batch.py:360-361
+    const unsigned am = __ballot_sync(0xffffffffu, active);
+    if (am) {
+      int slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(act_count, __popc(am));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      if (active) {
+        const int64_t slot = (int64_t)slot0 + __popc(am & ((1u << lane) - 1));
+        act_pid[slot] = (int32_t)pid;
+        act_idx2[slot] = bidx;
+        act_q[3 * slot] = qx; act_q[3 * slot + 1] = qy; act_q[3 * slot + 2] = qz;
+      }
+    }
+    if (valid) {
+      pts_mask[pid] = active ? 1.0f : 0.0f;
+      if (!active) reinterpret_cast<float4*>(raw)[pid] = make_float4(-80.f, -80.f, -80.f, -80.f);   // :493
+    }
+    // smpl_query / smpl_src rows (ref :483-484): q where active, zeros elsewhere
+    if (base + 32 <= n_points) {
+      stage[3 * lane] = active ? qx : 0.f; stage[3 * lane + 1] = active ? qy : 0.f; stage[3 * lane + 2] = active ? qz : 0.f;
+      __syncwarp();
+      if (lane < 24) {
+        reinterpret_cast<float4*>(smpl_query + 3 * base)[lane] = reinterpret_cast<const float4*>(stage)[lane];
+        reinterpret_cast<float4*>(smpl_src + 3 * base)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+    } else if (valid) {
+      smpl_query[3 * pid] = active ? qx : 0.f; smpl_query[3 * pid + 1] = active ? qy : 0.f; smpl_query[3 * pid + 2] = active ? qz : 0.f;
+      smpl_src[3 * pid] = 0.f; smpl_src[3 * pid + 1] = 0.f; smpl_src[3 * pid + 2] = 0.f;
+    }
+  }
+}
+
 }  // namespace mps
 
 extern "C" int mpsnerf_sample_knn(const float* rays, int64_t n_rays, int32_t S, const float* t_vals,
@@ -149,9 +291,26 @@ extern "C" int mpsnerf_sample_knn(const float* rays, int64_t n_rays, int32_t S, 
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(smpl_query) & 15) == 0 && (reinterpret_cast<uintptr_t>(smpl_src) & 15) == 0);
   int64_t blocks = (P + mps::kK1Threads - 1) / mps::kK1Threads;
   if (blocks > mps::kNumSMs * 8) blocks = mps::kNumSMs * 8;
-  mps::sample_knn_kernel<<<(int)blocks, mps::kK1Threads, 0, (cudaStream_t)stream>>>(
-      rays, P, S, t_vals, u, points, frame, static_cast<const char*>(grid_tp), raw, pts_mask, smpl_query,
-      smpl_src, act_pid, act_idx2, act_q, act_count);
+  static int form = -1;       // MPSNERF_K1 = warp (default) | block
+  if (form < 0) { const char* e = getenv("MPSNERF_K1"); form = (e && e[0] == 'b') ? 1 : 0; }
+  if (form == 1)
+    mps::sample_knn_kernel<<<(int)blocks, mps::kK1Threads, 0, (cudaStream_t)stream>>>(
+        rays, P, S, t_vals, u, points, frame, static_cast<const char*>(grid_tp), raw, pts_mask, smpl_query,
+        smpl_src, act_pid, act_idx2, act_q, act_count);
+  else {
+    // persistent warps: exactly as many blocks as are resident at once (no second, partial wave)
+    static int resident = 0;
+    if (resident == 0) {
+      int per_sm = 0;
+      MPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mps::sample_knn_warp_kernel, mps::kK1Threads, 0));
+      resident = mps::kNumSMs * (per_sm > 0 ? per_sm : 1);
+    }
+    const int64_t want = (P + mps::kK1Threads - 1) / mps::kK1Threads;
+    blocks = want < resident ? want : resident;
+    mps::sample_knn_warp_kernel<<<(int)blocks, mps::kK1Threads, 0, (cudaStream_t)stream>>>(
+        rays, P, S, t_vals, u, points, frame, static_cast<const char*>(grid_tp), raw, pts_mask, smpl_query,
+        smpl_src, act_pid, act_idx2, act_q, act_count);
+  }
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
 }

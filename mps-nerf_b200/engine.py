@@ -59,11 +59,35 @@ def pack_kmajor_sw128(w, n_pad=None, k_pad=None):
 
 
 class FrameContext:
-    """Device-resident state of one (source, target) pair."""
-    __slots__ = ("frame_dev", "grid_tp", "grid_tv", "latent", "img4", "skin_w", "n_views", "keep")
+    """Device-resident state of one (source, target) pair.
+
+    The preparation runs as three concurrent branches (engine._prepare_frame): the *front* (frame header + target-pose
+    grid: all K1 needs) on the caller's stream, the *LBS* branch (transform sets + template grid: needed from K3 on)
+    and the *trunk* branch (encoder latent + NHWC images: needed from K4 on) on side streams.  ``wait_lbs`` /
+    ``wait_trunk`` make the current stream wait for a branch; reading ``latent`` / ``img4`` waits for the trunk."""
+    __slots__ = ("frame_dev", "grid_tp", "grid_tv", "_latent", "_img4", "skin_w", "n_views", "keep", "ev_lbs", "ev_trunk")
+
+    def wait_lbs(self):
+        if self.ev_lbs is not None:
+            torch.cuda.current_stream().wait_event(self.ev_lbs)
+
+    def wait_trunk(self):
+        if self.ev_trunk is not None:
+            torch.cuda.current_stream().wait_event(self.ev_trunk)
+
+    @property
+    def latent(self):
+        self.wait_trunk()
+        return self._latent
+
+    @property
+    def img4(self):
+        self.wait_trunk()
+        return self._img4
 
     def frame_host(self):
         """Host copy of the device-side mpsnerf_frame (tests / debugging; synchronises)."""
+        self.wait_lbs()
         return _lib.Frame.from_buffer_copy(bytes(self.frame_dev.cpu().numpy()))
 
 
@@ -181,21 +205,51 @@ class RenderEngine:
 
     def _prepare_frame(self, sp, tp, smpl):
         """~45 small launches (trunk, layout changes, K0, two grid builds) whose GPU time is ~0.45 ms but whose
-        launch overhead is ~1 ms when issued one by one behind an idle GPU: the sequence is captured once per
-        (shape, device, weights) into a CUDA graph over static input / output buffers and replayed per frame.
+        launch overhead is ~1 ms when issued one by one behind an idle GPU: they are captured once per
+        (shape, device, weights) into THREE CUDA graphs over static input / output buffers -- front (frame header,
+        target-pose grid), LBS (transform sets, template grid), trunk (encoder, NHWC layouts) -- and replayed per
+        frame on three streams, so that K1 starts right behind the front and runs beside the trunk; K3 waits for the
+        LBS branch and K4 for the trunk (FrameContext.wait_*).
         A FrameContext therefore stays valid until the next prepare_frame of this engine (the network keeps a
-        single-entry frame cache, lib/skinnning_batch.py::frame_context).  MPSNERF_PREP_GRAPH=0 disables it."""
+        single-entry frame cache, lib/skinnning_batch.py::frame_context).  MPSNERF_PREP_GRAPH=0 disables the graphs
+        (same three branches, launched eagerly)."""
         dev = sp["img_all"].device
         V = sp["img_all"].shape[0]
-        assert 2 <= V <= _lib.MAX_VIEWS
+        vmax = _lib.MAX_VIEWS if self.precision == "fp32" else _lib.MAX_VIEWS_TC
+        if not 2 <= V <= vmax:      # checked before anything is enqueued (the dense kernels would fail late and vaguely)
+            raise ValueError(f"{V} input views: the {self.precision} path supports 2..{vmax} "
+                             f"(tensor-core path 2..{_lib.MAX_VIEWS_TC}, fp32 path 2..{_lib.MAX_VIEWS})")
         f32 = lambda t: t.reshape(-1).float().contiguous()
         ins = [sp["img_all"].float().contiguous()] + \
               [f32(tp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
               [f32(sp["params"][k]) for k in ("poses", "shapes", "R", "Th")] + \
               [f32(sp["R_all"]), f32(sp["T_all"]), f32(sp["K_all"]),
                tp["vertices"].float().contiguous(), sp["t_vertices"].float().contiguous()]
+        main = torch.cuda.current_stream()
+        sides = self._side.get(dev)
+        if sides is None:
+            sides = self._side[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(4))
+        s_lbs, s_trunk = sides[0], sides[1]
+        # a previous frame's branches may still be reading the static inputs / writing the static outputs
+        main.wait_stream(s_lbs)
+        main.wait_stream(s_trunk)
         if not self._use_prep_graph:
-            return self._prep_body(ins, smpl)
+            ctx = self._new_ctx(ins, smpl)
+            for st in (s_lbs, s_trunk):
+                st.wait_stream(main)
+            self._prep_front(ins, ctx)
+            with torch.cuda.stream(s_lbs):
+                self._prep_lbs(ins, ctx, sides[2])
+                ctx.ev_lbs = torch.cuda.Event()
+                ctx.ev_lbs.record()
+            with torch.cuda.stream(s_trunk):
+                self._prep_trunk(ins, ctx)
+                ctx._latent.record_stream(main)
+                ctx._img4.record_stream(main)
+                ctx.ev_trunk = torch.cuda.Event()
+                ctx.ev_trunk.record()
+            _lib.count_launches(4)
+            return ctx
         m = self.net.encoder_2d.model
         key = (str(dev), self.precision, id(smpl), tuple(tuple(t.shape) for t in ins),
                tuple(p._version for p in m.parameters()) + tuple(bf._version for bf in m.buffers()))
@@ -204,88 +258,122 @@ class RenderEngine:
             try:
                 static = [torch.empty_like(t) for t in ins]
                 torch._foreach_copy_(static, ins)
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):          # warm-up outside the capture (cuDNN plans, lazy inits)
-                    self._prep_body(static, smpl)
-                torch.cuda.current_stream().wait_stream(side)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    ctx = self._prep_body(static, smpl)
+                ctx = self._new_ctx(static, smpl)
+                warm = torch.cuda.Stream(device=dev)
+                warm.wait_stream(main)
+                with torch.cuda.stream(warm):          # warm-up outside the capture (cuDNN plans, lazy inits)
+                    self._prep_front(static, ctx)
+                    self._prep_lbs(static, ctx, sides[2])
+                    self._prep_trunk(static, ctx)
+                main.wait_stream(warm)
+                torch.cuda.synchronize(dev)
+                graphs = []
+                for body in (lambda: self._prep_front(static, ctx), lambda: self._prep_lbs(static, ctx, sides[2]),
+                             lambda: self._prep_trunk(static, ctx)):
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        body()
+                    graphs.append(gr)
                 if len(self._prep_graphs) >= 4:
                     self._prep_graphs.clear()
-                g = self._prep_graphs[key] = (graph, static, ctx)
-            except Exception:                          # capture not possible here: stay on the eager path
+                g = self._prep_graphs[key] = (graphs, static, ctx)
+            except RuntimeError as e:
+                # Only a capture limitation (an op that cannot be captured on this build / allocator state) sends
+                # the engine to the eager path, loudly; anything else -- bad inputs, OOM, a cuDNN failure -- is a
+                # real error and propagates.
+                msg = str(e)
+                if "captur" not in msg.lower() or "out of memory" in msg.lower():
+                    raise
+                import warnings
+                warnings.warn(f"mpsnerf_b200: CUDA-graph capture of the frame preparation failed ({msg.splitlines()[0]}); "
+                              "running it eagerly from now on (MPSNERF_PREP_GRAPH=0 silences this)")
                 self._use_prep_graph = False
                 torch.cuda.synchronize(dev)
-                return self._prep_body(ins, smpl)
-        graph, static, ctx = g
+                return self._prepare_frame(sp, tp, smpl)
+        graphs, static, ctx = g
         torch._foreach_copy_(static, ins)
-        graph.replay()
-        _lib.count_launches(3)
+        for st in (s_lbs, s_trunk):
+            st.wait_stream(main)
+        graphs[0].replay()                       # front: on the caller's stream, K1 follows it
+        with torch.cuda.stream(s_lbs):
+            graphs[1].replay()
+            ctx.ev_lbs = torch.cuda.Event()
+            ctx.ev_lbs.record()
+        with torch.cuda.stream(s_trunk):
+            graphs[2].replay()
+            ctx.ev_trunk = torch.cuda.Event()
+            ctx.ev_trunk.record()
+        _lib.count_launches(4)
         return ctx
 
-    def _prep_body(self, ins, smpl):
-        img_all, keep, verts, tverts = ins[0], ins[1:12], ins[12], ins[13]
+    def _new_ctx(self, ins, smpl):
+        """Allocate the outputs of the preparation (on the current stream) for the given (static) inputs."""
+        img_all, verts = ins[0], ins[12]
         dev = img_all.device
-        lib = self.lib
-        V = img_all.shape[0]
-        H, W = img_all.shape[-2:]
         ctx = FrameContext()
-        ctx.n_views = V
-        # Four independent branches (graph edges when captured): the encoder trunk on the current stream, K0, the
-        # target-pose grid and the template grid on side streams.  K0 and the grid builds are single-CTA kernels
-        # (~0.1 ms each, 0.2 ms when they share their SM with the trunk's convolutions) that would otherwise queue
-        # up behind the trunk or behind each other; the target grid needs only the raw Th / R of the target pose
-        # (K0 copies them into the frame unchanged), so it does not wait for K0.
-        main = torch.cuda.current_stream()
-        sides = self._side.get(dev)
-        if sides is None:
-            sides = self._side[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
-        tab = self._smpl_tables(smpl, dev)
-        ctx.skin_w = tab["weights"]
+        ctx.n_views = img_all.shape[0]
+        ctx.skin_w = self._smpl_tables(smpl, dev)["weights"]
         ctx.frame_dev = torch.empty(ctypes.sizeof(_lib.Frame), dtype=torch.uint8, device=dev)
-        nv = verts.shape[0]
-        gb = lib.mpsnerf_grid_bytes(nv)
+        gb = self.lib.mpsnerf_grid_bytes(verts.shape[0])
         ctx.grid_tp = torch.empty(gb, dtype=torch.uint8, device=dev)
         ctx.grid_tv = torch.empty(gb, dtype=torch.uint8, device=dev)
-        ctx.keep = list(ins)
-        Hf, Wf = ((H // 2 - 1) // 2 + 1, (W // 2 - 1) // 2 + 1)     # trunk output size: floor(H/2), then conv1 7x7 / 2 pad 3
-        for st in sides:
-            st.wait_stream(main)
-        with torch.cuda.stream(sides[0]):
-            # K0: LBS transforms (target / big / source pose), cameras -> mpsnerf_frame, all on the device
-            _lib.check(lib.mpsnerf_frame_prepare(*[_lib.ptr(t) for t in keep], V, W, H, Wf, Hf,
-                                                 _lib.ptr(tab["v_template"]), _lib.ptr(tab["shapedirs"]),
-                                                 _lib.ptr(tab["J_regressor"]), _lib.ptr(tab["parents"]),
-                                                 tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
-                       "frame_prepare")
-        with torch.cuda.stream(sides[1]):
-            # keep = [poses, shapes, R, Th](target), [poses, shapes, R, Th](source), R_all, T_all, K_all
-            _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, _lib.ptr(keep[3]), _lib.ptr(keep[2]), GRID_CELL_TARGET,
-                                              _lib.ptr(ctx.grid_tp), gb, _stream()), "grid_build(target)")
-        with torch.cuda.stream(sides[2]):
+        ctx.keep = (list(ins), smpl)
+        ctx._latent = ctx._img4 = ctx.ev_lbs = ctx.ev_trunk = None
+        return ctx
+
+    @staticmethod
+    def _feat_size(H, W):
+        return (H // 2 - 1) // 2 + 1, (W // 2 - 1) // 2 + 1     # trunk output size: floor(H/2), then conv1 7x7 / 2 pad 3
+
+    def _prep_front(self, ins, ctx):
+        """What K1 needs: the copied fields of the frame (Th / R of the target pose, cameras, sizes) and the grid over
+        the target-pose vertices in SMPL space (it reads the raw Th / R, not the frame)."""
+        img_all, keep, verts = ins[0], ins[1:12], ins[12]
+        lib = self.lib
+        H, W = img_all.shape[-2:]
+        Hf, Wf = self._feat_size(H, W)
+        # keep = [poses, shapes, R, Th](target), [poses, shapes, R, Th](source), R_all, T_all, K_all
+        _lib.check(lib.mpsnerf_frame_header(_lib.ptr(keep[2]), _lib.ptr(keep[3]), _lib.ptr(keep[6]), _lib.ptr(keep[7]),
+                                            _lib.ptr(keep[8]), _lib.ptr(keep[9]), _lib.ptr(keep[10]), ctx.n_views, W, H, Wf, Hf,
+                                            _lib.ptr(ctx.frame_dev), _stream()), "frame_header")
+        nv = verts.shape[0]
+        _lib.check(lib.mpsnerf_grid_build(_lib.ptr(verts), nv, _lib.ptr(keep[3]), _lib.ptr(keep[2]), GRID_CELL_TARGET,
+                                          _lib.ptr(ctx.grid_tp), ctx.grid_tp.numel(), _stream()), "grid_build(target)")
+
+    def _prep_lbs(self, ins, ctx, side):
+        """What K3 needs: the four LBS transform sets (K0, float64 -> fp32) and, beside it, the template grid."""
+        keep, tverts = ins[1:12], ins[13]
+        lib = self.lib
+        cur = torch.cuda.current_stream()
+        tab = self._smpl_tables(ctx.keep[1], tverts.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
             _lib.check(lib.mpsnerf_grid_build(_lib.ptr(tverts), tverts.shape[0], None, None, GRID_CELL_TEMPLATE,
-                                              _lib.ptr(ctx.grid_tv), gb, _stream()), "grid_build(template)")
-        # encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
-        # (cuDNN convolutions default to TF32; the fp32 precision mode keeps true fp32 end to end)
+                                              _lib.ptr(ctx.grid_tv), ctx.grid_tv.numel(), _stream()), "grid_build(template)")
+        _lib.check(lib.mpsnerf_frame_transforms(_lib.ptr(keep[0]), _lib.ptr(keep[1]), _lib.ptr(keep[4]), _lib.ptr(keep[5]),
+                                                _lib.ptr(tab["v_template"]), _lib.ptr(tab["shapedirs"]),
+                                                _lib.ptr(tab["J_regressor"]), _lib.ptr(tab["parents"]),
+                                                tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
+                   "frame_transforms")
+        cur.wait_stream(side)
+
+    def _prep_trunk(self, ins, ctx):
+        """What K4 needs: encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather
+        (cuDNN convolutions default to TF32; the fp32 precision mode keeps true fp32 end to end)."""
+        img_all = ins[0]
+        H, W = img_all.shape[-2:]
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=(self.precision != "fp32")):
             latent = self._encode(img_all)
-        assert latent.shape[-2:] == (Hf, Wf), (latent.shape, Hf, Wf)
-        ctx.latent = latent.permute(0, 2, 3, 1).contiguous().float()
-        ctx.img4 = F.pad(img_all.permute(0, 2, 3, 1), (0, 1)).contiguous().float()
-        for st in sides:
-            main.wait_stream(st)
-        if not torch.cuda.is_current_stream_capturing():
-            _lib.count_launches(3)
-        return ctx
+        assert latent.shape[-2:] == self._feat_size(H, W), (latent.shape, H, W)
+        ctx._latent = latent.permute(0, 2, 3, 1).contiguous().float()
+        ctx._img4 = F.pad(img_all.permute(0, 2, 3, 1), (0, 1)).contiguous().float()
 
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
     def run(self, ctx, rays8=None, S=1, t_vals=None, u=None, points=None, composite=True, occupancy=False,
             all_active=False):
         """rays8 (N,8) [o,d,near,far] or points (P,3).  Returns a dict of flat tensors."""
-        lib, dev = self.lib, ctx.latent.device
+        lib, dev = self.lib, ctx.frame_dev.device
         if points is not None:
             P, N = points.shape[0], points.shape[0]
             S = 1
@@ -369,6 +457,8 @@ class RenderEngine:
                 ws = self._buf("dense", lib.mpsnerf_dense_bf16_workspace(cap, V), dev)
             idx3 = self._buf("idx3", 4 * cap, dev).view(torch.int32) if dbg is not None else None
             xw = self._buf("xw", 12 * cap, dev).view(torch.float32) if dbg is not None else None
+        if n_act > done_upto:
+            ctx.wait_lbs()
         for first in range(done_upto, n_act, slab):
             cnt = min(slab, n_act - first)
             with self.span("k3_deform"):
@@ -376,6 +466,7 @@ class RenderEngine:
                 _lib.ptr(act_pid), _lib.ptr(act_idx2), _lib.ptr(act_q), first, cnt, _lib.ptr(ctx.skin_w),
                 _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.grid_tv), _lib.ptr(xc), _lib.ptr(uv), _lib.ptr(ss),
                 _lib.ptr(idx3), _lib.ptr(xw), 1 if all_active else 0, _stream()), "deform_project")
+            ctx.wait_trunk()
             with self.span("k4_gather"):
               if self.precision == "fp32":
                 _lib.check(lib.mpsnerf_gather_tokens(_lib.ptr(uv), cnt, V, _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.latent),
@@ -430,10 +521,12 @@ class RenderEngine:
         tokens = self._buf("tokens", 2 * ld * V * cap, dev).view(torch.float16)
         packed = self._packed_weights(dev)
         ws = self._buf("dense", lib.mpsnerf_dense_bf16_workspace(cap, V), dev)
+        ctx.wait_lbs()
         with self.span("k3_deform"):
             _lib.check(lib.mpsnerf_deform_project_dc(_lib.ptr(act_pid), _lib.ptr(act_idx2), _lib.ptr(act_q), 0, cap, _lib.ptr(counter),
                                                      _lib.ptr(ctx.skin_w), _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.grid_tv),
                                                      _lib.ptr(xc), _lib.ptr(uv), _lib.ptr(ss), _stream()), "deform_project_dc")
+        ctx.wait_trunk()
         with self.span("k4_gather"):
             _lib.check(lib.mpsnerf_gather_tokens_f16_dc(_lib.ptr(uv), 0, cap, _lib.ptr(counter), V, _lib.ptr(ctx.frame_dev),
                                                         _lib.ptr(ctx.latent), _lib.ptr(ctx.img4), _lib.ptr(tokens), _stream()),

@@ -19,8 +19,9 @@ def _host3(a, shape):
     return np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
 
 
-def gen_rays8(H, W, K, R, T, bounds, device="cuda"):
-    """-> rays8 (H*W, 8) float32 [o, d, near, far] and mask_at_box (H*W,) bool, on ``device``.
+def gen_rays8(H, W, K, R, T, bounds, device="cuda", rows=None):
+    """-> rays8 (n, 8) float32 [o, d, near, far] and mask_at_box (n,) bool, on ``device``; n = H*W, or
+    len(rows)*W when ``rows`` (int32 CUDA tensor / sequence of image-row indices) selects a subset of the view.
 
     Rays that do not cross the (0.01-widened) box exactly twice keep near = 0, far = 1
     (the full-frame convention of ``sample_ray_THuman``, ref :719-724)."""
@@ -28,13 +29,20 @@ def gen_rays8(H, W, K, R, T, bounds, device="cuda"):
     if dev.type != "cuda":
         raise RuntimeError("mpsnerf_b200 ray generation runs on CUDA devices only")
     K, R, T, b = _host3(K, (3, 3)), _host3(R, (3, 3)), _host3(T, (3,)), _host3(np.asarray(bounds, dtype=np.float32), (2, 3))
-    rays8 = torch.empty(int(H) * int(W), 8, device=dev)
-    mask = torch.empty(int(H) * int(W), dtype=torch.uint8, device=dev)
+    if rows is not None:
+        rows = torch.as_tensor(rows, dtype=torch.int32, device=dev).contiguous()
+    n = (int(H) if rows is None else int(rows.numel())) * int(W)
+    rays8 = torch.empty(n, 8, device=dev)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    cam = (K.ctypes.data_as(ctypes.c_void_p), R.ctypes.data_as(ctypes.c_void_p), T.ctypes.data_as(ctypes.c_void_p),
+           b.ctypes.data_as(ctypes.c_void_p))
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().mpsnerf_gen_rays(K.ctypes.data_as(ctypes.c_void_p), R.ctypes.data_as(ctypes.c_void_p),
-                                                 T.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
-                                                 int(H), int(W), _lib.ptr(rays8), _lib.ptr(mask),
-                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "gen_rays")
+        if rows is None:
+            _lib.check(_lib.load().mpsnerf_gen_rays(*cam, int(H), int(W), _lib.ptr(rays8), _lib.ptr(mask), st), "gen_rays")
+        else:
+            _lib.check(_lib.load().mpsnerf_gen_rays_rows(*cam, int(H), int(W), _lib.ptr(rows), int(rows.numel()),
+                                                         _lib.ptr(rays8), _lib.ptr(mask), st), "gen_rays_rows")
     _lib.count_launches(1)
     return rays8, mask.bool()
 

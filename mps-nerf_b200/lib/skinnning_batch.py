@@ -138,6 +138,7 @@ class SKinningBatch(nn.Module):
         if self._engine is None or self._engine.precision != self.precision:
             from ..engine import RenderEngine
             self._engine = RenderEngine(self, precision=self.precision)
+            self._frame_key = self._frame_ctx = None      # a context belongs to the engine that prepared it
         return self._engine
 
     def _smpl_for(self, gender):
@@ -147,16 +148,28 @@ class SKinningBatch(nn.Module):
     def invalidate_frame_cache(self):
         self._frame_key = None
 
+    @staticmethod
+    def _frame_inputs(sp_input, tp_input):
+        """Every input the prepared frame state depends on (engine._prepare_frame, K0, the two grids, the trunk)."""
+        sp, tp = sp_input["params"], tp_input["params"]
+        return (sp_input["img_all"], sp_input["R_all"], sp_input["T_all"], sp_input["K_all"], sp_input["t_vertices"],
+                sp["poses"], sp["shapes"], sp["R"], sp["Th"], tp_input["vertices"], tp["poses"], tp["shapes"], tp["R"],
+                tp["Th"], sp_input["gender"])
+
     def frame_context(self, sp_input, tp_input):
-        """Prepared per-frame state for already-squeezed dicts, cached on the tensors' identity."""
-        probe = (sp_input["img_all"], sp_input["params"]["poses"], sp_input["t_vertices"], tp_input["vertices"],
-                 tp_input["params"]["poses"], tp_input["params"]["Th"])
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in probe) + (self.training,)
+        """Prepared per-frame state for already-squeezed dicts, cached on the identity (storage, version, shape) of
+        EVERY tensor it was derived from, the engine that prepared it and the mode.  The cache holds one entry: with
+        the graph-captured preparation a context is a view of static buffers that the next prepare_frame of the same
+        engine overwrites, so an older context must never be handed out again."""
+        probe = self._frame_inputs(sp_input, tp_input)
+        eng = self.engine()
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if torch.is_tensor(t) else t for t in probe) + \
+            (self.training, id(eng), eng.precision)
         if key != self._frame_key:
             self._check_supported()
             if not sp_input["img_all"].is_cuda:
                 raise RuntimeError("mpsnerf_b200 has no CPU path: inputs must be CUDA tensors")
-            self._frame_ctx = self.engine().prepare_frame(sp_input, tp_input, self._smpl_for(sp_input["gender"]))
+            self._frame_ctx = eng.prepare_frame(sp_input, tp_input, self._smpl_for(sp_input["gender"]))
             self._frame_key = key
             self._frame_keep = probe
         return self._frame_ctx

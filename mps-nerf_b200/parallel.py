@@ -35,6 +35,42 @@ def balanced_ray_block(weights, rank, world):
     return cuts[rank], cuts[rank + 1]
 
 
+def interleaved_rows(H, rank, world, group=2):
+    """Image rows of ``rank`` when one H-row target view is dealt out to ``world`` GPUs in groups of ``group`` rows:
+    row r belongs to rank (r // group) % world.  Every rank then samples the whole image evenly, so the active
+    points -- which cluster on the body's silhouette -- balance by themselves (no profiling pass, no work
+    estimate), and each rank generates its own rays on the device from the camera (render(camera=dict(...,
+    rows=...))).  Returns an int32 tensor, ascending."""
+    r = torch.arange(int(H), dtype=torch.int32)
+    return r[((r // int(group)) % int(world)) == int(rank)].contiguous()
+
+
+def gather_rows_frame(block, H, W, group=2):
+    """all_gather per-ray outputs ``block (n_local_rows * W, ...)`` of an ``interleaved_rows`` split into the full
+    ``(H * W, ...)`` frame, rows back in image order (20 B/ray for rgb + disp + acc; optional -- the render path
+    itself needs no exchange)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return block
+    world = dist.get_world_size()
+    rows = [interleaved_rows(H, r, world, group) for r in range(world)]
+    width = max(len(r) for r in rows) * W
+    pad = torch.zeros(width, *block.shape[1:], dtype=block.dtype, device=block.device)
+    pad[:block.shape[0]] = block
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    out = torch.empty(H * W, *block.shape[1:], dtype=block.dtype, device=block.device)
+    out = out.reshape(H, W, *block.shape[1:])
+    for p, r in zip(parts, rows):
+        out[r.long().to(block.device)] = p[:len(r) * W].reshape(len(r), W, *block.shape[1:])
+    return out.reshape(H * W, *block.shape[1:])
+
+
+def grid_slab(n, rank, world):
+    """[z0, z1) of rank's slab when an n^3 density grid (extract_thuman_mesh.py:107-125) is split along its first
+    axis; slabs differ by at most one plane.  Points and the post-step are per point: no exchange."""
+    return ray_block(int(n), rank, world)
+
+
 def render_sharded(render_fn, rays, near, far, **kw):
     """Render this rank's block of ``rays (B,2,N,3)`` with ``render_fn`` (= run_nerf_batch.render).
 

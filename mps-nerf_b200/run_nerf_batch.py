@@ -194,11 +194,18 @@ def batchify_rays(rays_flat, chunk=1024 * 32, sp_input=None, tp_input=None, **kw
 
 
 def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.0, far=1.0,
-           sp_input=None, tp_input=None, use_viewdirs=False, **kwargs):
+           sp_input=None, tp_input=None, use_viewdirs=False, camera=None, **kwargs):
     """ref :100-135.  rays (B,2,N,3), near/far (B,N,1) -> [rgb_map, disp_map, acc_map, extras].
 
     The whole ray set goes through the kernels at once (they chunk internally by active
     points); ``chunk`` only determines the width of ``extras['other_loss']`` (4 per chunk).
+
+    ``camera`` (extension): instead of ``rays`` / ``near`` / ``far`` pass the target view itself,
+    ``dict(K=, R=, T=, bounds=, H=, W=[, rows=])`` -- the arguments of the reference's ``get_rays`` /
+    ``get_near_far`` (lib/if_nerf_data_utils.py:11-25, 55-92), which the datasets run in numpy per view.  The rays
+    are then generated on the device (csrc/raygen.cu; one subject, B = 1), nothing per-ray is uploaded, and
+    ``extras['mask_at_box']`` (N,) bool is returned as well.  ``rows`` restricts the view to a list of image rows
+    (how one frame is dealt out to several GPUs, parallel.interleaved_rows).
     """
     def pack(rays, near, far):
         rays_o, rays_d = rays[:, 0, ...], rays[:, 1, ...]
@@ -206,7 +213,6 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
         return torch.cat([torch.reshape(rays_o, [B, -1, 3]).float(), torch.reshape(rays_d, [B, -1, 3]).float(),
                           torch.reshape(near, [B, -1, 1]).float(), torch.reshape(far, [B, -1, 1]).float()], -1)
 
-    sh = rays[:, 1, ...].shape
     ready = None
     if not sp_input["img_all"].is_cuda:
         # host dicts (ideally pinned): upload only what the path reads, on the current stream (the frame
@@ -215,9 +221,19 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
             raise RuntimeError("mpsnerf_b200 has no CPU path: a CUDA device is required")
         dev = torch.device("cuda", torch.cuda.current_device())
         sp_input, tp_input = _upload_hot(sp_input, HOT_KEYS_SP, dev), _upload_hot(tp_input, HOT_KEYS_TP, dev)
-    if not rays.is_cuda and sp_input["img_all"].is_cuda:
+    box = None
+    if rays is None:
+        if camera is None:
+            raise ValueError("render() needs either rays / near / far or camera=dict(K, R, T, bounds, H, W)")
+        from .lib.if_nerf_data_utils import gen_rays8
+        rays8, box = gen_rays8(camera["H"], camera["W"], camera["K"], camera["R"], camera["T"], camera["bounds"],
+                               device=sp_input["img_all"].device, rows=camera.get("rows"))
+        packed = rays8[None]
+        sh = (1, packed.shape[1], 3)
+    elif not rays.is_cuda and sp_input["img_all"].is_cuda:
         # Host (ideally pinned) rays / near / far: uploaded and packed on a copy stream, so that the transfer
         # overlaps the per-frame preparation (trunk, K0, grids), which needs only sp_input / tp_input.
+        sh = rays[:, 1, ...].shape
         dev = sp_input["img_all"].device
         main = torch.cuda.current_stream(dev)
         cs = _copy_stream(dev)
@@ -228,6 +244,7 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
             ready.record(cs)
         packed.record_stream(main)
     else:
+        sh = rays[:, 1, ...].shape
         packed = pack(rays, near, far)
     n = packed.shape[1]
     ret = render_rays(packed, sp_input=sp_input, tp_input=tp_input, _rays_ready=ready, **kwargs)
@@ -235,6 +252,8 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
     ret["other_loss"] = torch.zeros(1, 4 * nchunks, device=packed.device)
     for k in ("rgb_map", "disp_map", "acc_map", "pts_mask", "raw"):
         ret[k] = torch.reshape(ret[k], list(sh[:-1]) + list(ret[k].shape[2:]))
+    if box is not None:
+        ret["mask_at_box"] = box
     keys = ("rgb_map", "disp_map", "acc_map")
     return [ret[k] for k in keys] + [{k: v for k, v in ret.items() if k not in keys}]
 

@@ -149,8 +149,24 @@ class Scene:
     """Container: ``smpl`` dict, ``sp_input``/``tp_input`` (batch dim 1), cameras and rays."""
 
 
+def smpl_by_gender(seed=0):
+    """The three SMPL-shaped models the reference loads at construction
+    (``lib/skinnning_batch.py:123-128``), built from the m/f/n template files."""
+    return {"male": make_smpl("m", seed), "female": make_smpl("f", seed), "neutral": make_smpl("n", seed)}
+
+
+def batch_scenes(scenes):
+    """Stack the input dicts of several same-sized scenes along the DataLoader batch dim (B > 1)."""
+    def cat(ds):
+        out = {}
+        for k, v in ds[0].items():
+            out[k] = cat([d[k] for d in ds]) if isinstance(v, dict) else torch.cat([d[k] for d in ds], 0)
+        return out
+    return cat([s.sp_input for s in scenes]), cat([s.tp_input for s in scenes])
+
+
 def make_scene(kind="thuman", seed=0, gender="n", H=None, W=None, n_views=3, novel_pose=False,
-               t_vertices_from="lbs"):
+               t_vertices_from="lbs", smpl_seed=None):
     """Build a seeded synthetic scene.
 
     kind: 'thuman' (512x512, f=640, inputs [4,12,20], target 1) or 'h36m'
@@ -158,7 +174,7 @@ def make_scene(kind="thuman", seed=0, gender="n", H=None, W=None, n_views=3, nov
     (focal scales with it) so that tests can use small images.
     """
     rng = np.random.RandomState(seed)
-    smpl = make_smpl(gender, seed)
+    smpl = make_smpl(gender, seed if smpl_seed is None else smpl_seed)
     base_hw, focal = (512, 640.0) if kind == "thuman" else (1000, 1150.0)
     H = H or base_hw
     W = W or base_hw
@@ -269,13 +285,16 @@ def inbox_ray_subset(scene, n):
     return ids[np.linspace(0, len(ids) - 1, n).astype(np.int64)]
 
 
-def seeded_state_dict(seed=0, alpha_gain=1.0):
+def seeded_state_dict(seed=0, alpha_gain=1.0, alpha_bias=None):
     """Deterministic weights for the *live* parameters (MLP, transformer, encoder trunk).
 
     Golden vectors cannot carry a 100 MB random-init checkpoint, so both the
     reference harness and the tests load this instead (``strict=False``).  The
     distribution is torch's default ``nn.Linear`` init; ``alpha_gain`` widens the
-    density head so that compositing is exercised with opaque surfaces.
+    density head so that compositing is exercised with opaque surfaces, and
+    ``alpha_bias`` (if given) replaces the bias of the density head: a large positive
+    value makes every active sample absorb, i.e. rays saturate (acc -> 1) within a few
+    samples of the surface.
     """
     g = np.random.RandomState(4242 + seed)
     sd = {}
@@ -290,6 +309,8 @@ def seeded_state_dict(seed=0, alpha_gain=1.0):
     for i, (o, k) in enumerate(dims):
         lin(f"pts_linears.{i}", o, k)
     lin("alpha_linear", 1, 256, gain=alpha_gain)
+    if alpha_bias is not None:
+        sd["alpha_linear.bias"] = torch.full((1,), float(alpha_bias))
     lin("feature_linear", 256, 256)
     lin("views_linear", 128, 411)
     lin("rgb_linear", 3, 128, gain=min(max(1.0, alpha_gain / 4), 20.0))

@@ -84,20 +84,60 @@ def _a12(A):
     return A[:, :3, :].reshape(24, 12).numpy().astype(F32)
 
 
-def frame_constants(smpl, sp, tp):
+def _rodrigues64(r):
+    """ref lib/run_nerf_helpers.py:174-192 in float64; r (24,3)."""
+    angle = np.sqrt(((r + 1e-8) ** 2).sum(1, keepdims=True))
+    k = r / angle
+    s, c = np.sin(angle)[:, :, None], (1.0 - np.cos(angle))[:, :, None]
+    z = np.zeros(len(r))
+    K = np.stack([z, -k[:, 2], k[:, 1], k[:, 2], z, -k[:, 0], -k[:, 1], k[:, 0], z], 1).reshape(-1, 3, 3)
+    return np.eye(3)[None] + s * K + c * np.einsum("nik,nkj->nij", K, K)
+
+
+def smpl_transforms64(smpl, poses, shapes):
+    """``smpl_transforms`` (ref lib/run_nerf_helpers.py:195-254) evaluated in float64 on the fp32 inputs and
+    rounded to fp32 once at the end: the arithmetic contract of K0 (csrc/frame_prep.cu).  Returns (24,12) fp32."""
+    f64 = lambda t: (t.detach().numpy() if torch.is_tensor(t) else np.asarray(t)).astype(F32).astype(np.float64)
+    v_shaped = f64(smpl["v_template"]) + (f64(smpl["shapedirs"]) * f64(shapes).reshape(1, 1, 10)).sum(2)
+    joints = f64(smpl["J_regressor"]) @ v_shaped
+    rot = _rodrigues64(f64(poses).reshape(24, 3))
+    parents = [int(p) for p in smpl["kintree_table"][0]]
+    G = np.zeros((24, 3, 4))
+    for j in range(24):
+        T = np.concatenate([rot[j], (joints[j] - (joints[parents[j]] if j else 0.0))[:, None]], 1)
+        if j == 0:
+            G[0] = T
+        else:
+            Gp = G[parents[j]]
+            G[j, :, :3] = Gp[:, :3] @ T[:, :3]
+            G[j, :, 3] = Gp[:, :3] @ T[:, 3] + Gp[:, 3]
+    A = G.copy()
+    A[:, :, 3] = G[:, :, 3] - np.einsum("jab,jb->ja", G[:, :, :3], joints)
+    return A.reshape(24, 12).astype(F32)
+
+
+def frame_constants(smpl, sp, tp, fp32_reference=False):
     """Everything that is computed once per (source, target) pair.
 
-    ``sp``/``tp`` are already squeezed (no batch dim).  Returns numpy fp32 arrays.
+    ``sp``/``tp`` are already squeezed (no batch dim).  Returns numpy fp32 arrays.  Default = the float64 ->
+    fp32 contract that K0 reproduces bit for bit; ``fp32_reference=True`` evaluates the same formulas with fp32
+    torch ops exactly as the reference does (the two agree to ~1 fp32 ulp: tests/test_oracle_vs_golden.py).
     """
     tpp, spp = tp["params"], sp["params"]
+    if fp32_reference:
+        xf = lambda poses, shapes: _a12(smpl_transforms(smpl, poses, shapes))
+        rinv = torch.inverse(spp["R"].reshape(3, 3)).numpy().astype(F32)
+    else:
+        xf = lambda poses, shapes: smpl_transforms64(smpl, poses, shapes)
+        rinv = np.linalg.inv(spp["R"].reshape(3, 3).numpy().astype(F32).astype(np.float64)).astype(F32)
     c = {
-        "A_tp": _a12(smpl_transforms(smpl, tpp["poses"], tpp["shapes"])),
-        "A_big_tp": _a12(smpl_transforms(smpl, big_pose(), tpp["shapes"])),
-        "A_big_sp": _a12(smpl_transforms(smpl, big_pose(), spp["shapes"])),
-        "A_sp": _a12(smpl_transforms(smpl, spp["poses"], spp["shapes"])),
+        "A_tp": xf(tpp["poses"], tpp["shapes"]),
+        "A_big_tp": xf(big_pose(), tpp["shapes"]),
+        "A_big_sp": xf(big_pose(), spp["shapes"]),
+        "A_sp": xf(spp["poses"], spp["shapes"]),
         "R_tp": tpp["R"].numpy().astype(F32).reshape(3, 3),
         "Th_tp": tpp["Th"].numpy().astype(F32).reshape(3),
-        "Rinv_sp": torch.inverse(spp["R"].reshape(3, 3)).numpy().astype(F32),
+        "Rinv_sp": rinv,
         "Th_sp": spp["Th"].numpy().astype(F32).reshape(3),
         "W": smpl["weights"].numpy().astype(F32),
         "t_vertices": sp["t_vertices"].numpy().astype(F32),
@@ -404,8 +444,9 @@ def raw2outputs(raw, z, rays_d, occupancy=False):
 
 
 def render(smpl, sd, sp_b, tp_b, rays_o, rays_d, near, far, S=64, u=None, bf16=False, chunk=4096,
-           return_stages=False):
-    """run_nerf_batch.render for one subject (ref :100-135, :401-444); numpy in, dict of numpy out."""
+           return_stages=False, occupancy=False, white_bkgd=False):
+    """run_nerf_batch.render for one subject (ref :100-135, :401-444); numpy in, dict of numpy out.
+    ``occupancy`` = --occupancy 1 (ref :383-386), ``white_bkgd`` = ref :394-396."""
     sp, tp = squeeze_inputs(sp_b, tp_b)
     c = frame_constants(smpl, sp, tp)
     latent = encode_images(sp["img_all"], sd)
@@ -422,7 +463,10 @@ def render(smpl, sd, sp_b, tp_b, rays_o, rays_d, near, far, S=64, u=None, bf16=F
             st["offset"] = s * S
             stages.append(st)
         out17[s:s + chunk] = r.reshape(-1, S, 17)
-    rgb, disp, acc, w, depth = raw2outputs(torch.from_numpy(out17[..., :4]), torch.from_numpy(z), torch.from_numpy(rays_d.astype(F32)))
+    rgb, disp, acc, w, depth = raw2outputs(torch.from_numpy(out17[..., :4]), torch.from_numpy(z), torch.from_numpy(rays_d.astype(F32)),
+                                           occupancy=occupancy)
+    if white_bkgd:
+        rgb = rgb + (1.0 - acc[..., None])
     res = {"rgb_map": rgb.numpy(), "disp_map": disp.numpy(), "acc_map": acc.numpy(), "depth_map": depth.numpy(),
            "raw": out17[..., :4], "pts_mask": out17[..., 4:5], "smpl_query_pts": out17[..., 11:14],
            "smpl_src_pts": out17[..., 14:17], "z_vals": z}

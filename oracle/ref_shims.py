@@ -139,13 +139,29 @@ def load_reference(n_samples=64, config="canonical_transformer.txt", extra=()):
 
 
 class ScatterLike(torch.nn.Module):
-    """Gives the net a ``.module`` and copies the input dicts per call, as DataParallel's
-    scatter does (the reference's ``sequeeze_0`` mutates them in place)."""
+    """Gives the net a ``.module`` and does what DataParallel's scatter / gather do around it (the reference's
+    only multi-subject mode, run_nerf_batch.py:344-350): every tensor of the input dicts and the points are
+    split along the batch dim into chunks of one subject, the module runs per chunk on a private copy of the
+    dicts (the reference's ``sequeeze_0`` mutates them in place), and the outputs are concatenated."""
 
     def __init__(self, net):
         super().__init__()
         self.module = net
 
+    @staticmethod
+    def _take(d, b):
+        out = {}
+        for k, v in d.items():
+            if isinstance(v, dict):
+                out[k] = ScatterLike._take(v, b)
+            elif torch.is_tensor(v) and v.dim() > 0:
+                out[k] = v[b:b + 1].clone()
+            else:
+                out[k] = v
+        return out
+
     def forward(self, sp, tp, pts, dirs):
-        import copy
-        return self.module(copy.deepcopy(sp), copy.deepcopy(tp), pts, dirs)
+        outs = []
+        for b in range(pts.shape[0]):
+            outs.append(self.module(self._take(sp, b), self._take(tp, b), pts[b:b + 1], None if dirs is None else dirs[b:b + 1]))
+        return torch.cat(outs, 0)

@@ -7,15 +7,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# scene kwargs of each golden case -- must match oracle/make_golden.py::CASES
-CASE_SCENES = {
-    "plain": dict(kind="thuman", seed=0),
-    "stress": dict(kind="thuman", seed=1, novel_pose=True),
-    "h36m": dict(kind="h36m", seed=2, H=500, W=500, novel_pose=True, t_vertices_from="file"),
-}
+from golden_cases import CASES, build_case, smpl_models  # noqa: E402  (table shared with oracle/make_golden.py)
+
+SINGLE_CASES = [n for n, c in CASES.items() if len(c["scenes"]) == 1]
 
 
 def pytest_configure(config):
@@ -36,16 +35,25 @@ _cache = {}
 
 
 def load_case(name):
-    """(scene, state_dict, golden npz dict) for a committed golden case."""
+    """(scene, state_dict, golden npz dict) for a committed single-subject golden case."""
     if name not in _cache:
-        from mpsnerf_b200 import synthetic
         g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
-        scene = synthetic.make_scene(**CASE_SCENES[name])
-        sd = synthetic.seeded_state_dict(scene.seed, float(g["alpha_gain"]))
-        _cache[name] = (scene, sd, g)
+        scenes, sd, _, _ = build_case(CASES[name])
+        assert len(scenes) == 1
+        _cache[name] = (scenes[0], sd, g)
     return _cache[name]
 
 
-@pytest.fixture(params=["plain", "stress", "h36m"])
+def load_batch_case(name):
+    """(scenes, state_dict, sp_input, tp_input, smpl models by gender, golden) for a B > 1 golden case."""
+    key = ("batch", name)
+    if key not in _cache:
+        g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+        scenes, sd, sp, tp = build_case(CASES[name])
+        _cache[key] = (scenes, sd, sp, tp, smpl_models(CASES[name]), g)
+    return _cache[key]
+
+
+@pytest.fixture(params=SINGLE_CASES)
 def case(request):
     return (request.param,) + load_case(request.param)

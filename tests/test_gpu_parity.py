@@ -121,16 +121,12 @@ def test_composite_against_oracle():
 
 
 # ------------------------------------------------------------------------------- stage parity vs oracle
-def _engine_consts(ctx, oc):
-    """Oracle frame constants with the per-frame matrices replaced by the ones the engine
-    uploaded, so that the bit-exact stages are compared on identical inputs."""
+def _frame_arrays(ctx):
     fr = ctx.frame_host()
-    c = dict(oc)
     f32 = lambda a, *s: np.array(list(a), dtype=np.float32).reshape(*s)
-    c.update(A_tp=f32(fr.A_tp, 24, 12), A_big_tp=f32(fr.A_big_tp, 24, 12), A_big_sp=f32(fr.A_big_sp, 24, 12),
-             A_sp=f32(fr.A_sp, 24, 12), R_tp=f32(fr.R_tp, 3, 3), Th_tp=f32(fr.Th_tp, 3),
-             Rinv_sp=f32(fr.Rinv_sp, 3, 3), Th_sp=f32(fr.Th_sp, 3))
-    return c
+    return dict(A_tp=f32(fr.A_tp, 24, 12), A_big_tp=f32(fr.A_big_tp, 24, 12), A_big_sp=f32(fr.A_big_sp, 24, 12),
+                A_sp=f32(fr.A_sp, 24, 12), R_tp=f32(fr.R_tp, 3, 3), Th_tp=f32(fr.Th_tp, 3),
+                Rinv_sp=f32(fr.Rinv_sp, 3, 3), Th_sp=f32(fr.Th_sp, 3))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -155,10 +151,11 @@ def test_stages_against_oracle(case, precision):
 
     smpl = O.smpl_tensors(scene.smpl)
     sp_c, tp_c = O.squeeze_inputs(scene.sp_input, scene.tp_input)
-    oc = O.frame_constants(smpl, sp_c, tp_c)
-    for k in ("A_tp", "A_big_tp", "A_big_sp", "A_sp"):
-        np.testing.assert_allclose(_engine_consts(ctx, oc)[k], oc[k], atol=2e-6)
-    c = _engine_consts(ctx, oc)
+    # K0 (csrc/frame_prep.cu) against the oracle's OWN frame constants: bit for bit (float64 -> fp32 contract), so
+    # everything below runs on the oracle's constants, not on values copied out of the engine
+    c = O.frame_constants(smpl, sp_c, tp_c)
+    for k, v in _frame_arrays(ctx).items():
+        assert np.array_equal(v, c[k]), (k, float(np.abs(v - c[k]).max()))
     z = O.sample_z(scene.near[ids], scene.far[ids], S, g.get("u"))
     pts = O.sample_points(scene.rays_o[ids], scene.rays_d[ids], z).reshape(-1, 3)
     latent = ctx.latent.permute(0, 3, 1, 2).cpu()          # the oracle consumes the same latent
@@ -197,20 +194,83 @@ def test_stages_against_oracle(case, precision):
 
 
 # ------------------------------------------------------------------------------- public API vs the reference's outputs
+def _configure(precision="bf16", occupancy=0):
+    """Install parser defaults + the flags a case needs (the reference parses them at import time)."""
+    from mpsnerf_b200 import run_nerf_batch as R
+    from mpsnerf_b200.parser_config import config_parser
+    return R.configure(config_parser().parse_args(["--precision", precision, "--occupancy", str(int(occupancy))]))
+
+
+def _check_render_vs_golden(rgb, disp, acc, extras, g, precision, S, spec):
+    """One subject's outputs of the public render() against what the UNMODIFIED reference produced."""
+    n = len(g["ray_ids"])
+    mask = extras["pts_mask"][..., 0].cpu().numpy() > 0.5
+    gmask = g["pts_mask"][..., 0] > 0
+    flips = mask != gmask                      # q via torch.mm in the reference vs pinned ops here
+    assert flips.sum() <= 2
+    if flips.any():                            # only where the reference's own d2 sits within rounding of the threshold
+        assert np.all(np.abs(g["d2_all"].reshape(n, S)[flips] - np.float32(0.05 ** 2)) < 5e-7)
+    good = ~flips.any(1)
+    both = mask & gmask
+    raw = extras["raw"].cpu().numpy()
+    scale = max(1.0, float(np.abs(g["raw"][gmask]).max()))
+    np.testing.assert_allclose(extras["smpl_query_pts"].cpu().numpy()[both], g["smpl_query_pts"][both], atol=2e-6)
+    close = np.isclose(extras["smpl_src_pts"].cpu().numpy()[both], g["smpl_src_pts"][both], atol=1e-4).all(-1)
+    assert close.mean() > 0.995            # the rest are nearest-vertex near-ties resolved differently by torch.mm/LU
+    sel = both.copy()
+    sel[both] = close
+    np.testing.assert_allclose(raw[sel], g["raw"][sel], atol=(5e-4 if precision == "fp32" else 3e-2) * scale)
+    assert np.all(raw[~mask] == -80.0)
+    ray_ok = good & ~(both & ~sel).any(1)
+    assert ray_ok.mean() > 0.97
+    rgb_n, acc_n = rgb.cpu().numpy(), acc.cpu().numpy()
+    d_rgb = np.abs(rgb_n[ray_ok] - g["rgb_map"][ray_ok])
+    d_acc = np.abs(acc_n[ray_ok] - g["acc_map"][ray_ok])
+    if precision == "fp32":
+        # 1e-4 is the north_star bound; the seeded rgb head has gain 20 at alpha_gain >= 80, where two fp32
+        # implementations that associate their matmuls differently already differ by ~3e-4 on opaque rays
+        # (the CPU oracle vs the reference shows the same: tests/test_oracle_vs_golden.py)
+        tol = 1e-4 if float(spec["alpha_gain"]) < 80 or "alpha_bias" not in spec else 5e-4
+        assert d_rgb.max() <= tol and d_acc.max() <= 1e-4, (d_rgb.max(), d_acc.max())
+    else:
+        assert d_rgb.max() <= 1e-2, d_rgb.max()
+        assert psnr(rgb_n[ray_ok], g["rgb_map"][ray_ok]) >= 45.0
+    # disp = 1/max(1e-10, depth/acc) is NaN exactly when acc == 0.  Rays without active samples must
+    # be NaN on both sides; rays whose acc is a few ulp from 0 (1 - exp(-tiny), GPU expf vs CPU exp)
+    # are degenerate and excluded from the pattern check.
+    dn, gn = disp.cpu().numpy()[ray_ok], g["disp_map"][ray_ok]
+    a_m, a_g = acc_n[ray_ok], g["acc_map"][ray_ok]
+    empty = ~gmask[ray_ok].any(1)
+    assert np.isnan(dn[empty]).all() and np.isnan(gn[empty]).all()
+    solid = np.minimum(a_m, a_g) > 1e-5
+    assert not np.isnan(dn[solid]).any() and not np.isnan(gn[solid]).any()
+    np.testing.assert_allclose(dn[solid], gn[solid], rtol=2e-2 if precision == "bf16" else 2e-3)
+    return int(ray_ok.sum())
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_render_against_reference_golden(case, precision):
+    """Public render() against the reference's own outputs: round-1 cases plus the opaque (acc > 0.99, stratified
+    jitter, white background), --occupancy 1 and full-size H36M (1000 x 1000 views) cases."""
+    from conftest import CASES
     from mpsnerf_b200 import run_nerf_batch as R, synthetic
     name, scene, sd, g = case
+    spec = CASES[name]
     net = R.NetworkHandle(make_net(scene, sd, precision))
     ids, S = g["ray_ids"], int(g["S"])
     rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
-    kw = dict(network_fn=net, network_query_fn=None, N_samples=S, perturb=1.0 if "u" in g else False, N_importance=0)
+    kw = dict(network_fn=net, network_query_fn=None, N_samples=S, perturb=1.0 if "u" in g else False, N_importance=0,
+              white_bkgd=bool(spec.get("white_bkgd", False)))
     if "u" in g:
         kw["perturb_u"] = torch.from_numpy(g["u"])[None].cuda()
     sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
-    rgb, disp, acc, extras = R.render(chunk=100, rays=rays, near=near, far=far, sp_input=sp, tp_input=tp,
-                                      use_viewdirs=True, **kw)
-    torch.cuda.synchronize()
+    _configure(precision, spec.get("occupancy", 0))
+    try:
+        rgb, disp, acc, extras = R.render(chunk=100, rays=rays, near=near, far=far, sp_input=sp, tp_input=tp,
+                                          use_viewdirs=True, **kw)
+        torch.cuda.synchronize()
+    finally:
+        _configure()
     assert rgb.shape == (1, len(ids), 3) and disp.shape == (1, len(ids)) and acc.shape == (1, len(ids))
     assert extras["raw"].shape == (1, len(ids), S, 4) and extras["pts_mask"].shape == (1, len(ids), S, 1)
     for k in ("smpl_query_pts", "smpl_src_pts", "correction", "correction_"):
@@ -218,39 +278,46 @@ def test_render_against_reference_golden(case, precision):
     assert extras["other_loss"].shape == (1, 4 * ((len(ids) + 99) // 100))
     # the caller's dicts are untouched (the reference mutates them)
     assert sp["img_all"].dim() == 5 and sp["gender"].shape == (1,)
-    mask = extras["pts_mask"][0, ..., 0].cpu().numpy() > 0.5
-    gmask = g["pts_mask"][..., 0] > 0
-    flips = mask != gmask                      # q via torch.mm in the reference vs pinned ops here
-    assert flips.sum() <= 2
-    good = ~flips.any(1)
-    both = mask & gmask
-    raw = extras["raw"][0].cpu().numpy()
-    scale = max(1.0, float(np.abs(g["raw"][gmask]).max()))
-    np.testing.assert_allclose(extras["smpl_query_pts"][0].cpu().numpy()[both], g["smpl_query_pts"][both], atol=2e-6)
-    close = np.isclose(extras["smpl_src_pts"][0].cpu().numpy()[both], g["smpl_src_pts"][both], atol=1e-4).all(-1)
-    assert close.mean() > 0.995            # the rest are nearest-vertex near-ties resolved differently by torch.mm/LU
-    sel = both.copy()
-    sel[both] = close
-    np.testing.assert_allclose(raw[sel], g["raw"][sel], atol=(5e-4 if precision == "fp32" else 3e-2) * scale)
-    assert np.all(raw[~mask] == -80.0)
-    ray_ok = good & ~(both & ~sel).any(1)
-    d_rgb = np.abs(rgb[0].cpu().numpy()[ray_ok] - g["rgb_map"][ray_ok])
-    d_acc = np.abs(acc[0].cpu().numpy()[ray_ok] - g["acc_map"][ray_ok])
-    if precision == "fp32":
-        assert d_rgb.max() <= 1e-4 and d_acc.max() <= 1e-4, (d_rgb.max(), d_acc.max())
-    else:
-        assert d_rgb.max() <= 1e-2, d_rgb.max()
-        assert psnr(rgb[0].cpu().numpy()[ray_ok], g["rgb_map"][ray_ok]) >= 45.0
-    # disp = 1/max(1e-10, depth/acc) is NaN exactly when acc == 0.  Rays without active samples must
-    # be NaN on both sides; rays whose acc is a few ulp from 0 (1 - exp(-tiny), GPU expf vs CPU exp)
-    # are degenerate and excluded from the pattern check.
-    dn, gn = disp[0].cpu().numpy()[ray_ok], g["disp_map"][ray_ok]
-    a_m, a_g = acc[0].cpu().numpy()[ray_ok], g["acc_map"][ray_ok]
-    empty = ~gmask[ray_ok].any(1)
-    assert np.isnan(dn[empty]).all() and np.isnan(gn[empty]).all()
-    solid = np.minimum(a_m, a_g) > 1e-5
-    assert not np.isnan(dn[solid]).any() and not np.isnan(gn[solid]).any()
-    np.testing.assert_allclose(dn[solid], gn[solid], rtol=2e-2 if precision == "bf16" else 2e-3)
+    if name in ("opaque", "occupancy"):
+        assert int((g["acc_map"] > 0.99).sum()) >= 90          # the case really saturates
+    _check_render_vs_golden(rgb[0], disp[0], acc[0], {k: v[0] for k, v in extras.items() if k != "other_loss"}, g,
+                            precision, S, spec)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_render_batch_and_gender_against_reference_golden(precision):
+    """B = 2 subjects in one render() call, genders 1 / 0 selecting the male / female SMPL tables
+    (lib/skinnning_batch.py:335-340), against the reference run under a DataParallel-style scatter."""
+    from conftest import CASES, load_batch_case
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    from mpsnerf_b200.lib import skinnning_batch as SB
+    scenes, sd, sp, tp, models, g = load_batch_case("batch2")
+    spec = CASES["batch2"]
+    net = make_net(scenes[0], sd, precision)       # constructs with scene 0's model ...
+    SB.set_default_smpl_models(models)             # ... so rebuild with the three gender tables
+    net = SB.SKinningBatch(human_sample=1, use_f2d=1, use_trans=1, smooth_loss=1, num_instances=25, mean_shape=0,
+                           correction_field=0, skinning_field=0, data_set_type="THuman_B", append_rgb=1,
+                           with_viewdirs=0, precision=precision)
+    net.load_state_dict(sd, strict=False)
+    handle = R.NetworkHandle(net.cuda().eval())
+    S = int(g["S"])
+    parts = [synthetic.rays_tensor(sc, g["ray_ids"][b], device="cuda") for b, sc in enumerate(scenes)]
+    rays, near, far = (torch.cat([p[k] for p in parts], 0) for k in range(3))
+    _configure(precision)
+    rgb, disp, acc, extras = R.render(rays=rays, near=near, far=far, sp_input=_cuda_dict(sp), tp_input=_cuda_dict(tp),
+                                      network_fn=handle, N_samples=S, perturb=False, use_viewdirs=True)
+    torch.cuda.synchronize()
+    n = g["ray_ids"].shape[1]
+    assert rgb.shape == (2, n, 3) and extras["raw"].shape == (2, n, S, 4) and extras["pts_mask"].shape == (2, n, S, 1)
+    for b in range(2):
+        gb = {k: v[b] for k, v in g.items() if k in ("ray_ids", "rgb_map", "disp_map", "acc_map", "raw", "pts_mask",
+                                                     "smpl_query_pts", "smpl_src_pts")}
+        gb["d2_all"] = g[f"d2_all_{b}"]
+        ok = _check_render_vs_golden(rgb[b], disp[b], acc[b], {k: v[b] for k, v in extras.items() if k != "other_loss"},
+                                     gb, precision, S, spec)
+        assert ok > 150
+    # the two subjects really differ (different bodies, poses and rays)
+    assert not torch.equal(extras["pts_mask"][0], extras["pts_mask"][1])
 
 
 # ------------------------------------------------------------------------------- edge cases and full-size properties
@@ -322,11 +389,13 @@ def test_network_fn_direct_and_extract_mesh():
 
 @pytest.mark.parametrize("precision", ["bf16"])
 def test_full_frame_properties(precision):
-    """BASELINE config 2 size (512x512 rays x 64 samples): determinism, sub-range invariance and
-    an oracle spot check on rays drawn from the full-frame result."""
+    """BASELINE config 2 size (512x512 rays x 64 samples) with the BENCH's own weights (alpha_gain = 300):
+    determinism, sub-range invariance and a spot check of rays drawn from the full-frame result against the
+    oracle's fp32 result (the north_star bound: rgb max-abs <= 1e-2, PSNR >= 45 dB; mask exact)."""
     from mpsnerf_b200 import run_nerf_batch as R, synthetic
     from oracle import oracle as O
-    scene, sd, g = load_case("plain")
+    scene = load_case("plain")[0]
+    sd = synthetic.seeded_state_dict(0, 300.0)          # == bench.py::build_scene_and_net
     net = R.NetworkHandle(make_net(scene, sd, precision))
     sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
     rays, near, far = synthetic.rays_tensor(scene, None, device="cuda")
@@ -338,14 +407,56 @@ def test_full_frame_properties(precision):
     n_act = int(a[3]["pts_mask"].sum())
     assert 0.02 < n_act / (512 * 512 * 64) < 0.2
     assert bool((a[3]["raw"][a[3]["pts_mask"][..., 0] == 0] == -80).all())
-    ids = np.random.RandomState(1).choice(512 * 512, 1024, replace=False)
-    ids.sort()
+    assert float(a[2].max()) > 0.5                       # the bench frame is not a translucent haze
+    # in-box rays: out-of-box ones (near 0, far 1) never come near the body
+    box = np.nonzero(scene.mask_at_box)[0]
+    ids = np.sort(np.random.RandomState(1).choice(box, 1024, replace=False))
     r = O.render(O.smpl_tensors(scene.smpl), sd, scene.sp_input, scene.tp_input, scene.rays_o[ids], scene.rays_d[ids],
-                 scene.near[ids], scene.far[ids], S=64, bf16=(precision == "bf16"))
+                 scene.near[ids], scene.far[ids], S=64, bf16=False)
     m = a[3]["pts_mask"][0, ids, :, 0].cpu().numpy() > 0.5
-    assert (m != (r["pts_mask"][..., 0] > 0.5)).sum() <= 2       # encoder on GPU vs CPU does not touch the mask
-    d = np.abs(a[0][0, ids].cpu().numpy() - r["rgb_map"])
-    assert d.max() <= 1e-2 and psnr(a[0][0, ids].cpu().numpy(), r["rgb_map"]) >= 45.0
+    assert np.array_equal(m, r["pts_mask"][..., 0] > 0.5)        # mask vs the oracle: exact
+    assert m.sum() > 3000
+    got = a[0][0, ids].cpu().numpy()
+    d = np.abs(got - r["rgb_map"])
+    assert d.max() <= 1e-2 and psnr(got, r["rgb_map"]) >= 45.0, (d.max(), psnr(got, r["rgb_map"]))
+    assert np.abs(a[2][0, ids].cpu().numpy() - r["acc_map"]).max() <= 1e-2
+
+
+def test_network_fn_and_extract_mesh_bf16():
+    """The tensor-core path through network_fn(sp, tp, pts, dirs) and the extract_mesh mode (every point evaluated,
+    canonical = the query point), against the oracle's fp32 result at the bench weight scale."""
+    from oracle import oracle as O
+    from mpsnerf_b200 import synthetic
+    scene = load_case("plain")[0]
+    sd = synthetic.seeded_state_dict(0, 300.0)
+    net = make_net(scene, sd, "bf16")
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+    v = scene.tp_input["vertices"][0].numpy()
+    rng = np.random.RandomState(5)
+    pts = (v[rng.randint(0, 6890, 3000)] + rng.normal(0, 0.03, (3000, 3))).astype(np.float32)
+    out = net(sp, tp, torch.from_numpy(pts)[None].cuda(), None)
+    assert out.shape == (1, 3000, 17)
+    smpl = O.smpl_tensors(scene.smpl)
+    sp_c, tp_c = O.squeeze_inputs(scene.sp_input, scene.tp_input)
+    ref = O.forward_points(smpl, sd, sp_c, tp_c, pts)
+    o = out[0].cpu().numpy()
+    act = ref[:, 4] > 0
+    assert np.array_equal(o[:, 4], ref[:, 4]) and act.sum() > 1000
+    assert np.array_equal(o[:, 11:], ref[:, 11:])            # smpl_query / smpl_src: pinned arithmetic, exact
+    scale = max(1.0, float(np.abs(ref[act, :4]).max()))
+    np.testing.assert_allclose(o[act, :4], ref[act, :4], atol=3e-2 * scale)
+    assert np.all(o[~act, :4] == -80.0) and not o[:, 5:11].any()
+    net.set_extract_mesh(True)
+    tv = scene.sp_input["t_vertices"][0].numpy()
+    cpts = (tv[rng.randint(0, 6890, 2000)] + rng.normal(0, 0.02, (2000, 3))).astype(np.float32)
+    out = net(sp, tp, torch.from_numpy(cpts)[None].cuda(), None)
+    assert out.shape == (1, 2000, 4)
+    ref = O.forward_points(smpl, sd, sp_c, tp_c, cpts, extract_mesh=True)
+    scale = max(1.0, float(np.abs(ref).max()))
+    np.testing.assert_allclose(out[0].cpu().numpy(), ref, atol=3e-2 * scale)
+    # density as the mesh extraction consumes it (extract_thuman_mesh.py:125): shifted softplus of channel 3
+    sig = lambda x: np.logaddexp(0.0, x - 1.0)
+    np.testing.assert_allclose(sig(out[0, :, 3].cpu().numpy()), sig(ref[:, 3]), atol=3e-2 * scale)
 
 
 # ------------------------------------------------------------------------------- ray generation (SURVEY 8f rank 1)
@@ -459,7 +570,7 @@ def test_other_view_counts_against_oracle(n_views):
                                       use_viewdirs=True)
         mask = ex["pts_mask"][0, ..., 0].cpu().numpy() > 0.5
         assert ex["raw"].shape[1] == 160 and scene.sp_input["img_all"].shape[1] == n_views
-        assert (mask != (ref["pts_mask"][..., 0] > 0.5)).sum() <= 1 and mask.sum() > 200
+        assert np.array_equal(mask, ref["pts_mask"][..., 0] > 0.5) and mask.sum() > 200      # exact
         assert float(np.abs(rgb[0].cpu().numpy() - ref["rgb_map"]).max()) <= tol
         assert float(np.abs(acc[0].cpu().numpy() - ref["acc_map"]).max()) <= tol
 

@@ -35,6 +35,12 @@ def _worker(rank, world, port, n_rays, out):
     ref = _fake_render(rays, near, far)
     assert torch.equal(full_rgb, ref[0]) and torch.equal(full_acc, ref[2])
     assert parallel.max_over_ranks(rank + 1.5, "cpu") == world + 0.5
+    # one frame dealt out by interleaved row groups: every rank fills its own rows, the gathered frame is whole
+    H, W = 37, 5
+    frame = torch.arange(H * W * 3, dtype=torch.float32).reshape(H * W, 3)
+    rows = parallel.interleaved_rows(H, rank, world, group=2)
+    mine = frame.reshape(H, W, 3)[rows.long()].reshape(-1, 3)
+    assert torch.equal(parallel.gather_rows_frame(mine, H, W, group=2), frame)
     dist.barrier()
     dist.destroy_process_group()
     out.put(rank)
@@ -49,6 +55,22 @@ def test_ray_blocks_partition():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
             sizes = [e - s for s, e in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_interleaved_rows_partition_and_grid_slabs():
+    from mpsnerf_b200.parallel import grid_slab, interleaved_rows
+    for H in (1, 2, 7, 512, 1000):
+        for w in (1, 2, 4, 8):
+            for group in (1, 2, 4):
+                parts = [interleaved_rows(H, r, w, group) for r in range(w)]
+                allr = torch.cat(parts)
+                assert allr.dtype == torch.int32 and sorted(allr.tolist()) == list(range(H))
+                if H >= 64 * w:            # even shares to within one row group
+                    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= group
+    for n in (1, 5, 256):
+        for w in (1, 2, 8):
+            slabs = [grid_slab(n, r, w) for r in range(w)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == n and all(slabs[i][1] == slabs[i + 1][0] for i in range(w - 1))
 
 
 def test_balanced_blocks_partition():

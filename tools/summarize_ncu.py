@@ -70,9 +70,14 @@ def full(src, dst):
         for r in data:
             f.write(f"\n== {short(r[ki])}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n")
             for k in KEYS:
-                if k in hdr:
-                    i = hdr.index(k)
-                    f.write(f"{k:<96}{r[i]:>18} {units[i]}\n")
+                # some metrics come back section-prefixed ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime...",
+                # the tensor-PIPE activity -- not to be confused with sm__mem_tensor_*, tensor-MEMORY activity): match
+                # the exact name or any "<section>.<name>" column, and say so when a requested metric is absent
+                cols = [i for i, h in enumerate(hdr) if h == k or h.endswith("." + k)]
+                if not cols:
+                    f.write(f"{k:<96}{'(not in report)':>18}\n")
+                for i in cols:
+                    f.write(f"{hdr[i]:<96}{r[i]:>18} {units[i]}\n")
     print(open(dst).read())
 
 
