@@ -82,7 +82,7 @@ def workload_config(workload, world, strong):
     return {"workload": w[2], "samples_per_ray": 64, "input_views": 3, "image": w[3],
             "network": "configs/%s (skinning_batch), seeded random weights (synthetic.seeded_state_dict(0, 300))" % w[1],
             "extras": "full reference contract (raw, pts_mask, smpl_query_pts, smpl_src_pts)",
-            "includes": "per-frame prep + encoder trunk + K1..K6", "l2": "flushed between timed steps (512 MiB fill)",
+            "includes": "per-frame prep + encoder trunk + K1..K6", "l2": "flushed in front of every timed step (512 MiB fill, outside the step's event pair)",
             "parallelism": (f"ONE target view dealt out to {world} GPUs in interleaved groups of 2 image rows, rays generated "
                             f"on each GPU from the camera; no data-path collective" if strong
                             else f"one target view per GPU x{world}")}
@@ -206,21 +206,26 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, collective=True):
+        """K steps, each bracketed by its own CUDA-event pair on the launch stream, the L2 flushed (512 MiB fill)
+        in front of every step OUTSIDE its event pair.  The host does not synchronise between steps -- it enqueues
+        ahead, as a renderer streaming frames does -- so a step's time is its device time, not the host's launch
+        latency behind an idle GPU; sum over the K steps, max over ranks."""
         for _ in range(warmup):
             fn()
         if collective:
             barrier()
         else:
             torch.cuda.synchronize()
-        ms = []
+        evs = []
         for _ in range(steps):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
             e1.record()
-            e1.synchronize()
-            ms.append(e0.elapsed_time(e1))
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = [e0.elapsed_time(e1) for e0, e1 in evs]
         if not collective:
             return sum(ms), ms
         barrier()

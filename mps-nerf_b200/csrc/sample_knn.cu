@@ -4,8 +4,9 @@
 //  * sample_knn_warp_kernel (default): warp-autonomous.  A warp owns 32 consecutive sample points per iteration
 //    and never meets a block barrier: every lane generates its point, moves it to SMPL space (pinned fp32) and
 //    tests one bit of the dilated occupancy bitmap; the survivors ("candidates", ~15 % of a frame) are searched
-//    four at a time, eight lanes per candidate -- a lane scans one x-run of the 27-cell neighbourhood (lane 0 of
-//    a group two), the (d2, index) minimum is reduced with three shuffle steps -- and the active points are
+//    four at a time, eight lanes per candidate -- the group walks the nine x-runs of the 27-cell neighbourhood
+//    together, runs beyond the mask radius pruned, vertices dealt out eight at a time; the (d2, index) minimum is
+//    reduced with three shuffle steps -- and the active points are
 //    compacted with one ballot and one atomicAdd per warp.  Per-point outputs are written straight from
 //    registers (raw / mask) or through a 384-byte per-warp staging row (smpl_query, so that the stores are
 //    128-bit and coalesced).
@@ -18,6 +19,8 @@
 namespace mps {
 
 constexpr int kK1Threads = 256;
+constexpr int kStrip = 8;             // chunks of 32 points per warp strip (warp-autonomous kernel)
+constexpr int kK1QueueBytes = (kK1Threads / 32) * 5 * kStrip * 32 * 4;
 
 __global__ void __launch_bounds__(kK1Threads)
 sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const float* __restrict__ t_vals,
@@ -159,8 +162,20 @@ sample_knn_warp_kernel(const float* __restrict__ rays, int64_t n_points, int S, 
   float* stage = s_stage[wid];
   const int64_t nchunks = (n_points + 31) >> 5;
   constexpr int kWarps = kK1Threads / 32;
+  // A warp works through strips of kStrip consecutive chunks (256 points = 4 rays at S = 64) and queues the strip's
+  // active points in shared memory; the queue is flushed with ONE atomicAdd and coalesced stores per strip.  The
+  // active list then keeps runs of up to 256 points' worth of spatial neighbours -- K3 and K4 read it 32 entries per
+  // warp and their grid / texture reads coalesce only if those are neighbours (per-chunk flushes interleave the
+  // chunks of 700 concurrent warps: K3 +23 %) -- and the atomic traffic on the one counter drops 8x.
+  extern __shared__ __align__(16) int32_t s_queue_all[];                 // [kWarps][5][kStrip * 32]
+  int32_t* q_pid = s_queue_all + wid * (5 * kStrip * 32);
+  int32_t* q_idx = q_pid + kStrip * 32;
+  float* q_q = reinterpret_cast<float*>(q_idx + kStrip * 32);          // [3][kStrip * 32], struct of arrays
+  const int64_t nstrips = (nchunks + kStrip - 1) / kStrip;
 
-  for (int64_t c = (int64_t)blockIdx.x * kWarps + wid; c < nchunks; c += (int64_t)gridDim.x * kWarps) {
+  for (int64_t strip = (int64_t)blockIdx.x * kWarps + wid; strip < nstrips; strip += (int64_t)gridDim.x * kWarps) {
+   int qn = 0;
+   for (int64_t c = strip * kStrip; c < min((strip + 1) * kStrip, nchunks); ++c) {
     const int64_t base = c << 5, pid = base + lane;
     const bool valid = pid < n_points;
     // ---- every lane: its point in SMPL space, one bitmap test
@@ -208,16 +223,37 @@ sample_knn_warp_kernel(const float* __restrict__ rays, int64_t n_points, int S, 
       const int ccx = __shfl_sync(0xffffffffu, cx, sl), ccy = __shfl_sync(0xffffffffu, cy, sl), ccz = __shfl_sync(0xffffffffu, cz, sl);
       float d = INF;
       int id = 0x7fffffff;
-      const int x0 = max(ccx - 1, 0), x1 = min(ccx + 1, h.nx - 1);
-      if (src >= 0 && x0 <= x1) {
-#pragma unroll 1
-        for (int rr = sub; rr < 9; rr += 8) {          // x-run rr = (dy, dz); lane 0 of the group also takes run 8
-          const int y = ccy + (rr % 3) - 1, z = ccz + (rr / 3) - 1;
-          if ((unsigned)y >= (unsigned)h.ny || (unsigned)z >= (unsigned)h.nz) continue;
+      if (src >= 0) {
+        // The eight lanes of a group walk the nine x-runs of the candidate's 27-cell neighbourhood together, a run's
+        // vertices dealt out eight at a time (the runs are uneven -- a cell on a hand holds 100+ vertices, most
+        // hold one or two -- so a lane per run would leave the warp waiting for its longest run).  A run, or the
+        // outer cells of a run, is skipped when a lower bound of its distance to the query already exceeds the
+        // mask radius: only vertices with d2 < r^2 can make the point active or be its nearest vertex.  Bound =
+        // gap to the cell face shrunk by 1e-3 cell (covers the rounding of the binning and of the pinned d2), the
+        // same rule as nn_search27 with cap = r^2.
+        const float m = 1e-3f * h.cell;
+        const float fx = sx - (h.ox + (float)ccx * h.cell), fy = sy - (h.oy + (float)ccy * h.cell),
+                    fz = sz - (h.oz + (float)ccz * h.cell);
+        float gl, gr;
+        gl = fmaxf(fx - m, 0.f); gr = fmaxf(h.cell - fx - m, 0.f);
+        const float gxl = gl * gl, gxr = gr * gr;
+        gl = fmaxf(fy - m, 0.f); gr = fmaxf(h.cell - fy - m, 0.f);
+        const float gyl = gl * gl, gyr = gr * gr;
+        gl = fmaxf(fz - m, 0.f); gr = fmaxf(h.cell - fz - m, 0.f);
+        const float gzl = gl * gl, gzr = gr * gr;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const int dy = k % 3 - 1, dz = k / 3 - 1;
+          const int y = ccy + dy, z = ccz + dz;
+          const float rowd2 = (dy < 0 ? gyl : (dy > 0 ? gyr : 0.f)) + (dz < 0 ? gzl : (dz > 0 ? gzr : 0.f));
+          if ((unsigned)y >= (unsigned)h.ny || (unsigned)z >= (unsigned)h.nz || rowd2 > kMaskThresh) continue;
+          const int x0 = max(ccx - ((gxl + rowd2 > kMaskThresh) ? 0 : 1), 0);
+          const int x1 = min(ccx + ((gxr + rowd2 > kMaskThresh) ? 0 : 1), h.nx - 1);
+          if (x0 > x1) continue;
           const int row = (z * h.ny + y) * h.nx;
           const int b = __ldg(&g.cell_start[row + x0]);
           const int e = __ldg(&g.cell_start[row + x1 + 1]);
-          for (int i = b; i < e; ++i) {
+          for (int i = b + sub; i < e; i += 8) {
             const float4 v = __ldg(&g.sorted[i]);
             nn_update(dist2_pinned(sx, sy, sz, v.x, v.y, v.z), __float_as_int(v.w), d, id);
           }
@@ -242,17 +278,13 @@ sample_knn_warp_kernel(const float* __restrict__ rays, int64_t n_points, int S, 
     // ---- outputs and compaction
     const bool active = valid && (bd2 < kMaskThresh);     // lib/skinnning_batch.py:360-361
     const unsigned am = __ballot_sync(0xffffffffu, active);
-    if (am) {
-      int slot0 = 0;
-      if (lane == 0) slot0 = atomicAdd(act_count, __popc(am));
-      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-      if (active) {
-        const int64_t slot = (int64_t)slot0 + __popc(am & ((1u << lane) - 1));
-        act_pid[slot] = (int32_t)pid;
-        act_idx2[slot] = bidx;
-        act_q[3 * slot] = qx; act_q[3 * slot + 1] = qy; act_q[3 * slot + 2] = qz;
-      }
+    if (active) {
+      const int slot = qn + __popc(am & ((1u << lane) - 1));
+      q_pid[slot] = (int32_t)pid;
+      q_idx[slot] = bidx;
+      q_q[slot] = qx; q_q[kStrip * 32 + slot] = qy; q_q[2 * kStrip * 32 + slot] = qz;
     }
+    qn += __popc(am);
     if (valid) {
       pts_mask[pid] = active ? 1.0f : 0.0f;
       if (!active) reinterpret_cast<float4*>(raw)[pid] = make_float4(-80.f, -80.f, -80.f, -80.f);   // :493
@@ -270,6 +302,23 @@ sample_knn_warp_kernel(const float* __restrict__ rays, int64_t n_points, int S, 
       smpl_query[3 * pid] = active ? qx : 0.f; smpl_query[3 * pid + 1] = active ? qy : 0.f; smpl_query[3 * pid + 2] = active ? qz : 0.f;
       smpl_src[3 * pid] = 0.f; smpl_src[3 * pid + 1] = 0.f; smpl_src[3 * pid + 2] = 0.f;
     }
+   }
+   // ---- flush the strip's queue: one atomicAdd, coalesced stores
+   __syncwarp();
+   if (qn) {
+     int slot0 = 0;
+     if (lane == 0) slot0 = atomicAdd(act_count, qn);
+     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+     for (int i = lane; i < qn; i += 32) {
+       act_pid[slot0 + i] = q_pid[i];
+       act_idx2[slot0 + i] = q_idx[i];
+     }
+     for (int i = lane; i < 3 * qn; i += 32) {      // act_q rows are (x, y, z): element i = component i % 3 of entry i / 3
+       const int e = i / 3, k = i - 3 * e;
+       act_q[3 * (int64_t)slot0 + i] = q_q[k * (kStrip * 32) + e];
+     }
+   }
+   __syncwarp();
   }
 }
 
@@ -302,12 +351,13 @@ extern "C" int mpsnerf_sample_knn(const float* rays, int64_t n_rays, int32_t S, 
     static int resident = 0;
     if (resident == 0) {
       int per_sm = 0;
-      MPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mps::sample_knn_warp_kernel, mps::kK1Threads, 0));
+      MPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mps::sample_knn_warp_kernel, mps::kK1Threads,
+                                                             mps::kK1QueueBytes));
       resident = mps::kNumSMs * (per_sm > 0 ? per_sm : 1);
     }
     const int64_t want = (P + mps::kK1Threads - 1) / mps::kK1Threads;
     blocks = want < resident ? want : resident;
-    mps::sample_knn_warp_kernel<<<(int)blocks, mps::kK1Threads, 0, (cudaStream_t)stream>>>(
+    mps::sample_knn_warp_kernel<<<(int)blocks, mps::kK1Threads, mps::kK1QueueBytes, (cudaStream_t)stream>>>(
         rays, P, S, t_vals, u, points, frame, static_cast<const char*>(grid_tp), raw, pts_mask, smpl_query,
         smpl_src, act_pid, act_idx2, act_q, act_count);
   }
