@@ -235,9 +235,9 @@ class RenderEngine:
         main.wait_stream(s_trunk)
         if not self._use_prep_graph:
             ctx = self._new_ctx(ins, smpl)
-            for st in (s_lbs, s_trunk):
-                st.wait_stream(main)
             self._prep_front(ins, ctx)
+            for st in (s_lbs, s_trunk):          # behind the front: its single-CTA grid build runs alone (3x faster)
+                st.wait_stream(main)
             with torch.cuda.stream(s_lbs):
                 self._prep_lbs(ins, ctx, sides[2])
                 ctx.ev_lbs = torch.cuda.Event()
@@ -292,9 +292,17 @@ class RenderEngine:
                 return self._prepare_frame(sp, tp, smpl)
         graphs, static, ctx = g
         torch._foreach_copy_(static, ins)
-        for st in (s_lbs, s_trunk):
-            st.wait_stream(main)
+        # The side branches start BEHIND the front (default): its single-CTA grid build then runs alone (3x faster than
+        # beside the trunk's convolutions), and the trunk / LBS kernels fill in beside K1 as its short-lived blocks
+        # retire.  MPSNERF_PREP_ORDER=together starts all three branches at once (A/B).
+        front_first = os.environ.get("MPSNERF_PREP_ORDER", "front_first") != "together"
+        if not front_first:
+            for st in (s_lbs, s_trunk):
+                st.wait_stream(main)
         graphs[0].replay()                       # front: on the caller's stream, K1 follows it
+        if front_first:
+            for st in (s_lbs, s_trunk):
+                st.wait_stream(main)
         with torch.cuda.stream(s_lbs):
             graphs[1].replay()
             ctx.ev_lbs = torch.cuda.Event()
