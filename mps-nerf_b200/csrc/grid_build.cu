@@ -17,6 +17,7 @@ __device__ __forceinline__ float3 load_vertex(const float* __restrict__ verts, i
 }
 
 constexpr int kBuildThreads = 1024;
+constexpr int kBuildSmemInts = 51200;      // 200 KB of dynamic shared memory
 
 __global__ void __launch_bounds__(kBuildThreads, 1)
 grid_build_kernel(const float* __restrict__ verts, int nv, const float* __restrict__ Th,
@@ -30,6 +31,7 @@ grid_build_kernel(const float* __restrict__ verts, int nv, const float* __restri
   __shared__ float s_red[6][32];
   __shared__ GridHdr s_hdr;
   __shared__ int s_scan[kBuildThreads / 32];
+  extern __shared__ int s_cells[];        // kBuildSmemInts ints: [cursor | cell_start] when the grid is small enough
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   // 1. bounding box
@@ -73,6 +75,13 @@ grid_build_kernel(const float* __restrict__ verts, int nv, const float* __restri
   }
   __syncthreads();
   const GridHdr g = s_hdr;
+  // The build is one CTA walking several dependent phases over per-cell arrays; with those arrays in shared memory
+  // (cells <= kBuildSmemInts / 2 - 1: 25 K cells; a posed body at 5 cm cells has ~15-20 K) every phase runs at
+  // shared-memory latency instead of L2 latency -- the target-pose build sits on the frame's critical path in front
+  // of K1 (160 us -> see DESIGN.md).  Larger grids work in the global arrays directly, as before.
+  const bool in_smem = 2 * (g.ncells + 1) <= kBuildSmemInts;
+  int* const cell_start_g = cell_start;
+  if (in_smem) { cursor = s_cells; cell_start = s_cells + g.ncells + 1; }
 
   // 2. histogram
   for (int c = tid; c < g.ncells; c += kBuildThreads) cursor[c] = 0;
@@ -129,24 +138,25 @@ grid_build_kernel(const float* __restrict__ verts, int nv, const float* __restri
     sorted[pos] = make_float4(v.x, v.y, v.z, __int_as_float(i));
   }
 
-  // 5. dilated occupancy bitmap: bit c set iff some cell of c's 27-neighbourhood holds a vertex
+  // 5. dilated occupancy bitmap: bit c set iff some cell of c's 27-neighbourhood holds a vertex.  One thread per
+  // cell, a warp's 32 consecutive cells form one word (ballot).
   const int nwords = (g.ncells + 31) / 32;
-  for (int w = tid; w < nwords; w += kBuildThreads) {
-    uint32_t bits = 0;
-    for (int b = 0; b < 32; ++b) {
-      int c = w * 32 + b;
-      if (c >= g.ncells) break;
-      int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
-      bool any = false;
+  for (int w = wid; w < nwords; w += kBuildThreads / 32) {
+    const int c = w * 32 + lane;
+    bool any = false;
+    if (c < g.ncells) {
+      const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
       for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1) && !any; ++z)
         for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1) && !any; ++y) {
-          int row = (z * g.ny + y) * g.nx;
+          const int row = (z * g.ny + y) * g.nx;
           any = cell_start[row + min(cx + 1, g.nx - 1) + 1] > cell_start[row + max(cx - 1, 0)];
         }
-      bits |= (any ? 1u : 0u) << b;
     }
-    occ[w] = bits;
+    const uint32_t bits = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) occ[w] = bits;
   }
+  if (in_smem)
+    for (int c = tid; c <= g.ncells; c += kBuildThreads) cell_start_g[c] = cell_start[c];
 }
 
 // Vertices clamped into the last cell (coordinate == bbox max) keep the neighbourhood
@@ -187,8 +197,10 @@ extern "C" int mpsnerf_grid_build(const float* verts, int n_verts, const float* 
   MPS_REQUIRE(cell > 0.f);
   MPS_REQUIRE(grid_bytes >= mpsnerf_grid_bytes(n_verts));
   MPS_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
-  mps::grid_build_kernel<<<1, mps::kBuildThreads, 0, (cudaStream_t)stream>>>(verts, n_verts, Th, R, cell,
-                                                                            static_cast<char*>(grid));
+  const size_t smem = sizeof(int) * (size_t)mps::kBuildSmemInts;
+  MPS_CUDA(cudaFuncSetAttribute(mps::grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mps::grid_build_kernel<<<1, mps::kBuildThreads, smem, (cudaStream_t)stream>>>(verts, n_verts, Th, R, cell,
+                                                                               static_cast<char*>(grid));
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
 }

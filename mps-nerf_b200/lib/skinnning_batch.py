@@ -116,6 +116,7 @@ class SKinningBatch(nn.Module):
         self._engine = None
         self._frame_key = None
         self._frame_ctx = None
+        self._gender_cache = {}
 
     # ------------------------------------------------------------------ reference API
     def set_extract_mesh(self, flag):
@@ -142,8 +143,26 @@ class SKinningBatch(nn.Module):
         return self._engine
 
     def _smpl_for(self, gender):
-        g = int(gender.reshape(-1)[0].item()) if torch.is_tensor(gender) else int(gender)
-        return self.SMPL_MALE if g == 1 else (self.SMPL_FEMALE if g == 0 else self.SMPL_NEU)   # :335-340
+        """SMPL tables of ``sp_input['gender']`` (1 male, 0 female, else neutral; :335-340).  The choice is made on the
+        host (it selects table pointers), so a device-resident gender costs one device -> host read -- a full
+        synchronisation, ~0.4 ms of idle GPU at the start of a frame -- which is paid once per tensor: the value is
+        cached on the tensor's identity (storage address, version; the cache holds a reference, so the address is not
+        reused while the entry lives)."""
+        if torch.is_tensor(gender):
+            if gender.is_cuda:
+                key = (gender.data_ptr(), gender._version, gender.device.index)
+                hit = self._gender_cache.get(key)
+                if hit is None:
+                    if len(self._gender_cache) > 64:
+                        self._gender_cache.clear()
+                    # the entry keeps the tensor alive: its address cannot be handed to another tensor while cached
+                    hit = self._gender_cache[key] = (int(gender.reshape(-1)[0].item()), gender)
+                g = hit[0]
+            else:
+                g = int(gender.reshape(-1)[0].item())
+        else:
+            g = int(gender)
+        return self.SMPL_MALE if g == 1 else (self.SMPL_FEMALE if g == 0 else self.SMPL_NEU)
 
     def invalidate_frame_cache(self):
         self._frame_key = None

@@ -58,7 +58,10 @@ def _select(d, b):
     out = {}
     for k, v in d.items():
         if torch.is_tensor(v):
-            out[k] = v[b].float() if v.dim() > 0 else v
+            if not v.is_floating_point():      # gender / indices: a view (keeps the storage identity the gender cache
+                out[k] = v[b] if v.dim() > 0 else v      # keys on; a dtype conversion would also cost a launch each)
+            else:
+                out[k] = v[b].float() if v.dim() > 0 else v
         elif isinstance(v, dict):
             out[k] = _select(v, b)
         else:
@@ -163,7 +166,8 @@ def _upload_hot(d, keys, dev):
         if isinstance(v, dict):
             return {k: mv(x) for k, x in v.items()}
         return v
-    return {k: mv(d[k]) for k in keys if k in d}
+    # gender stays on the host: it only selects which SMPL tables to use, a host-side decision
+    return {k: (d[k] if k == "gender" else mv(d[k])) for k in keys if k in d}
 
 
 def hot_input_bytes(sp_input, tp_input):
