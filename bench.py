@@ -242,7 +242,7 @@ def run_ours(a):
     launches = (_lib.LAUNCHES - l0) * a.steps // (a.steps + warm)
     clocks = sampler.stop()
     e2e_ms, _ = timed(step_e2e, a.steps, 2)
-    e2e_host_ms, _ = timed(step_e2e_host_rays, max(a.steps // 2, 2), 1)
+    e2e_host_ms, _ = timed(step_e2e_host_rays, max(a.steps // 2, 2), 2)
 
     # per-stage device times of the same step (separate passes, CUDA events on the launch stream)
     eng = net.engine()

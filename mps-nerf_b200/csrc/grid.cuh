@@ -103,49 +103,6 @@ __device__ __forceinline__ void nn_search27_all(const GridHdr& h, const int* __r
   }
 }
 
-// The same scan restricted to what can matter below a fixed radius: an x-run, or the outer cells of a run, is
-// skipped when a lower bound of its distance to the query exceeds `cap` -- callers that only care about vertices
-// with d2 < cap (K1: the human-region mask radius; a point is active only if its nearest vertex is that close, and
-// then that vertex is inside the kept cells).  The bound is the gap to the cell face shrunk by 1e-3 cell (covers
-// the rounding of the binning formula, ~1e-6 cell, and of the pinned d2) and the test is strict, so no vertex that
-// could pass d2 < cap, or tie with one, is skipped.  Unlike nn_search27 below the bound does not depend on the best
-// distance so far: the nine runs stay independent (their loads overlap) -- this is the variant for latency-bound K1.
-// A sphere of radius r fills 16 % of the 3 x 3 x 3-cell box of side 3.03 r; cell-granular pruning keeps ~40 %.
-__device__ __forceinline__ void nn_search27_cap(const GridHdr& h, const int* __restrict__ cell_start,
-                                                const float4* __restrict__ sorted, int cx, int cy, int cz,
-                                                float qx, float qy, float qz, float cap, float& bd2, int& bidx) {
-  const float m = 1e-3f * h.cell;
-  const float fx = qx - (h.ox + (float)cx * h.cell), fy = qy - (h.oy + (float)cy * h.cell),
-              fz = qz - (h.oz + (float)cz * h.cell);
-  float gl, gr;
-  gl = fmaxf(fx - m, 0.f); gr = fmaxf(h.cell - fx - m, 0.f);
-  const float gxl = gl * gl, gxr = gr * gr;
-  gl = fmaxf(fy - m, 0.f); gr = fmaxf(h.cell - fy - m, 0.f);
-  const float gyl = gl * gl, gyr = gr * gr;
-  gl = fmaxf(fz - m, 0.f); gr = fmaxf(h.cell - fz - m, 0.f);
-  const float gzl = gl * gl, gzr = gr * gr;
-  for (int dz = -1; dz <= 1; ++dz) {
-    const int z = cz + dz;
-    const float zd2 = dz < 0 ? gzl : (dz > 0 ? gzr : 0.f);
-    if ((unsigned)z >= (unsigned)h.nz || zd2 > cap) continue;
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int y = cy + dy;
-      const float rowd2 = zd2 + (dy < 0 ? gyl : (dy > 0 ? gyr : 0.f));
-      if ((unsigned)y >= (unsigned)h.ny || rowd2 > cap) continue;
-      const int x0 = max(cx - ((gxl + rowd2 > cap) ? 0 : 1), 0);
-      const int x1 = min(cx + ((gxr + rowd2 > cap) ? 0 : 1), h.nx - 1);
-      if (x0 > x1) continue;
-      const int row = (z * h.ny + y) * h.nx;
-      const int b = __ldg(&cell_start[row + x0]);
-      const int e = __ldg(&cell_start[row + x1 + 1]);
-      for (int i = b; i < e; ++i) {
-        const float4 v = __ldg(&sorted[i]);
-        nn_update(dist2_pinned(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w), bd2, bidx);
-      }
-    }
-  }
-}
-
 // Nearest vertex of the 27-cell neighbourhood of (cx,cy,cz), exact, with pruning: the nine x-runs (rows) are
 // visited nearest first -- the query's own row, the four rows sharing a face with it, the four diagonal ones --
 // and a row, or the outer cell of a row, is skipped when a lower bound of its distance to the query already

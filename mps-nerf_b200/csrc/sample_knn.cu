@@ -22,7 +22,7 @@ sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const
                   const mpsnerf_frame* __restrict__ frame, const char* __restrict__ grid_buf,
                   float* __restrict__ raw, float* __restrict__ pts_mask, float* __restrict__ smpl_query,
                   float* __restrict__ smpl_src, int32_t* __restrict__ act_pid, int32_t* __restrict__ act_idx2,
-                  float* __restrict__ act_q, int32_t* __restrict__ act_count, int prune) {
+                  float* __restrict__ act_q, int32_t* __restrict__ act_count) {
   const GridView g = grid_view(grid_buf);
   __shared__ GridHdr s_hdr;
   __shared__ float s_fr[12];                 // Th(3) R(9)
@@ -89,13 +89,8 @@ sample_knn_kernel(const float* __restrict__ rays, int64_t n_points, int S, const
       const float cxq = s_q[3 * t], cyq = s_q[3 * t + 1], czq = s_q[3 * t + 2];
       float bd2 = INF;
       int bidx = 0x7fffffff;
-      // MPSNERF_K1_PRUNE=0: the plain nine-run scan (A/B); default: runs beyond the mask radius are skipped
-      if (prune)
-        nn_search27_cap(h, g.cell_start, g.sorted, cell_coord(cxq, h.ox, h.inv_cell), cell_coord(cyq, h.oy, h.inv_cell),
-                        cell_coord(czq, h.oz, h.inv_cell), cxq, cyq, czq, kMaskThresh, bd2, bidx);
-      else
-        nn_search27_all(h, g.cell_start, g.sorted, cell_coord(cxq, h.ox, h.inv_cell), cell_coord(cyq, h.oy, h.inv_cell),
-                        cell_coord(czq, h.oz, h.inv_cell), cxq, cyq, czq, bd2, bidx);
+      nn_search27_all(h, g.cell_start, g.sorted, cell_coord(cxq, h.ox, h.inv_cell), cell_coord(cyq, h.oy, h.inv_cell),
+                      cell_coord(czq, h.oz, h.inv_cell), cxq, cyq, czq, bd2, bidx);
       s_d2[t] = bd2;
       s_idx[t] = bidx;
     }
@@ -158,14 +153,13 @@ extern "C" int mpsnerf_sample_knn(const float* rays, int64_t n_rays, int32_t S, 
   // batch -- short-lived blocks, so that the rest of the frame preparation (encoder trunk, LBS transforms, template
   // grid), which the engine launches beside K1 on other streams, gets SM slots as K1's blocks retire instead of
   // queueing behind a resident grid.
-  static int persistent = -1, prune = -1;
+  static int persistent = -1;
   if (persistent < 0) { const char* e = getenv("MPSNERF_K1_GRID"); persistent = (e && e[0] == 'p') ? 1 : 0; }
-  if (prune < 0) { const char* e = getenv("MPSNERF_K1_PRUNE"); prune = (e && e[0] == '0') ? 0 : 1; }
   int64_t blocks = (P + mps::kK1Threads - 1) / mps::kK1Threads;
   if (persistent && blocks > mps::kNumSMs * 8) blocks = mps::kNumSMs * 8;
   mps::sample_knn_kernel<<<(unsigned)blocks, mps::kK1Threads, 0, (cudaStream_t)stream>>>(
       rays, P, S, t_vals, u, points, frame, static_cast<const char*>(grid_tp), raw, pts_mask, smpl_query,
-      smpl_src, act_pid, act_idx2, act_q, act_count, prune);
+      smpl_src, act_pid, act_idx2, act_q, act_count);
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
 }
