@@ -345,6 +345,121 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_train(a):
+    """--workload train = BASELINE configs[3]: one optimisation step (render forward in training mode, backward,
+    gradient all-reduce, Adam) on 1024 rays per GPU x 64 samples x 3 views, data-parallel replicas (weak scaling)."""
+    from mpsnerf_b200 import _lib, synthetic
+    from mpsnerf_b200 import run_nerf_batch as R
+    from mpsnerf_b200.train import TrainStep
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    _lib.check(_lib.load().mpsnerf_check_device(local), "check_device")
+    scene, net, args = build_scene_and_net("fp32", None, "thuman")
+    args.smooth_loss = 0
+    R.configure(args)
+    handle = R.NetworkHandle(net).to(dev).train()
+    n_rays, S = 1024, 64
+    box = np.nonzero(scene.mask_at_box)[0]
+    ids = np.sort(np.random.RandomState(100 + rank).choice(box, n_rays, replace=False))      # every rank its own batch
+    rays_h, near_h, far_h = (t.pin_memory() for t in synthetic.rays_tensor(scene, ids))
+    rng = np.random.RandomState(7 + rank)
+    tgt_h = torch.from_numpy(rng.uniform(0, 1, (1, n_rays, 3)).astype(np.float32)).pin_memory()
+    msk_h = torch.from_numpy((rng.uniform(0, 1, (1, n_rays, 1)) > 0.5).astype(np.float32)).pin_memory()
+    u_h = torch.from_numpy(rng.uniform(0, 1, (1, n_rays, S)).astype(np.float32)).pin_memory()
+    pin = lambda d: {k: (v.pin_memory() if torch.is_tensor(v) else pin(v) if isinstance(v, dict) else v) for k, v in d.items()}
+    to_dev = lambda d: {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else to_dev(v) if isinstance(v, dict) else v) for k, v in d.items()}
+    sp_h, tp_h = pin(scene.sp_input), pin(scene.tp_input)
+    sp_d, tp_d = to_dev(sp_h), to_dev(tp_h)
+    res_d = [t.to(dev) for t in (rays_h, near_h, far_h, tgt_h, msk_h, u_h)]
+    opt = torch.optim.Adam(list(net.parameters()), lr=args.lrate, betas=(0.9, 0.999))
+    ts = TrainStep(handle, opt, acc_loss=bool(args.acc_loss))
+    kw = dict(N_samples=S, perturb=1.0, use_viewdirs=True, chunk=args.chunk)
+    loss_h = torch.empty(1).pin_memory()
+
+    def step_resident():
+        rays, near, far, tgt, msk, u = res_d
+        return ts.step(R.render, rays=rays, near=near, far=far, sp_input=sp_d, tp_input=tp_d, target_rgb=tgt, bkgd_msk=msk,
+                       perturb_u=u, **kw)
+
+    def step_e2e():
+        rays, near, far, tgt, msk, u = (t.to(dev, non_blocking=True) for t in (rays_h, near_h, far_h, tgt_h, msk_h, u_h))
+        sp, tp = R._upload_hot(sp_h, R.HOT_KEYS_SP, dev), R._upload_hot(tp_h, R.HOT_KEYS_TP, dev)
+        loss = ts.step(R.render, rays=rays, near=near, far=far, sp_input=sp, tp_input=tp, target_rgb=tgt, bkgd_msk=msk,
+                       perturb_u=u, **kw)
+        loss_h.copy_(loss.reshape(1), non_blocking=True)
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    warm = max(a.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.LAUNCHES
+    total_ms = timed(step_resident, a.steps, warm)
+    launches = (_lib.LAUNCHES - l0) * a.steps // (a.steps + warm)
+    clocks = sampler.stop()
+    e2e_ms = timed(step_e2e, a.steps, 2)
+    h2d = R.hot_input_bytes(sp_h, tp_h) + sum(t.numel() * 4 for t in (rays_h, near_h, far_h, tgt_h, msk_h, u_h))
+    n_grad = sum(p.numel() for p in net.parameters() if p.grad is not None)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    print(json.dumps({
+        "metric": "rays/sec (training step: fwd + bwd + grad all-reduce + Adam)", "value": n_rays * world * a.steps / (total_ms * 1e-3),
+        "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": total_ms / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "train_thuman_512x512_V3_1024rays_S64", "rays_per_gpu_per_step": n_rays, "samples_per_ray": S,
+                   "input_views": 3, "image": "512x512", "loss": "img2mse(rgb) + img2mse(acc), smooth term off, perturb = 1",
+                   "optimizer": "Adam", "l2": "flushed in front of every timed step (512 MiB fill, outside the step's event pair)",
+                   "parallelism": f"data-parallel replicas x{world}: one NCCL all-reduce of the dense-stage gradient bucket "
+                                  f"(launched inside the backward, overlapping the cuDNN trunk backward) + one of the trunk gradients"},
+        "e2e": {"value": n_rays * world * a.steps / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / a.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "live_gradient_floats": int(n_grad),
+        "active_points": int(net.train_engine().eng.last_active)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(budget_s=20.0, n_rays=None, steps=1, warmup=0, workload="thuman"):
     """Time the reference algorithm on the host cores on in-box rays of the bench scene (BASELINE config 1 shape):
     the UNMODIFIED reference under import shims when its tree is present ($MPSNERF_REF, /root/reference,
@@ -409,12 +524,14 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MPSNERF_PRECISION", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["train"],
                     help="default: thuman (BASELINE configs[1]) on 1 GPU, h36m (configs[2]) on several")
     ap.add_argument("--mode", default="auto", choices=["auto", "strong", "weak"],
                     help="N > 1: strong = ONE frame split over the GPUs (default), weak = one target view per GPU")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "train":
+        run_train(a)
     else:
         run_ours(a)

@@ -190,6 +190,35 @@ int mpsnerf_dense_fp32(const float* tokens, int32_t ld, const float* xc, int64_t
                        int n_views, const float* const* weights, const int32_t* act_pid,
                        int64_t first, float* raw, void* workspace, void* stream);
 
+/* ---- training step: the dense stage with saved intermediates, and the backward of K6 / dense / K4 -----------
+ * Replaces what autograd does for the reference's training step (run_nerf_batch.py:544-570:
+ * render -> img2mse(rgb) + img2mse(acc) -> loss.backward()) on the render path.  fp32 on CUDA cores: a training
+ * batch is ~1 K rays / ~5 K active points per GPU.  Under the shipped configs (skinning_field = correction_field = 0)
+ * no parameter sits upstream of the canonical points, so K1 / K3 have no backward; gradients reach the live
+ * transformer + MLP parameters (mpsnerf_dense_train_bwd) and, through the latent, the encoder trunk
+ * (mpsnerf_gather_tokens_bwd -> torch / cuDNN).
+ *  - dense_train_fwd: as mpsnerf_dense_fp32, but writes out4 (count, 4) = [rgb, alpha] per active point instead
+ *    of scattering, and keeps every intermediate in `workspace` (>= mpsnerf_dense_train_workspace bytes) for
+ *  - dense_train_bwd: d_out4 (count, 4) -> `grads` (46 device pointers in the order of `weights`, each ACCUMULATED
+ *    into) and d_tokens (count, V, 155) (overwritten);
+ *  - composite_bwd: d_rgb (n_rays, 3), d_acc (n_rays, may be NULL) -> d_raw (n_rays, S, 4) (overwritten; zero for the
+ *    -80-filled samples of masked-out points); same sampling arguments as mpsnerf_composite;
+ *  - gather_tokens_bwd: scatter-add of d_tokens[:, :, 0:128] (row stride ld) into d_latent (V, Hf, Wf, 128), which the
+ *    caller zeroes; the RGB half of a token depends on the input images only;
+ *  - rows4_gather / rows4_scatter: dst[i] = src[act_pid[i]] / dst[act_pid[i]] = src[i] on float4 rows (raw <-> out4). */
+size_t mpsnerf_dense_train_workspace(int64_t count, int n_views);
+int mpsnerf_dense_train_fwd(const float* tokens, int32_t ld, const float* xc, int64_t count, int n_views,
+                            const float* const* weights, float* out4, void* workspace, void* stream);
+int mpsnerf_dense_train_bwd(const float* d_out4, int64_t count, int n_views, const float* const* weights,
+                            float* const* grads, float* d_tokens, void* workspace, void* stream);
+int mpsnerf_composite_bwd(const float* raw, const float* rays, int64_t n_rays, int32_t S, const float* t_vals,
+                          const float* u, const float* z_vals, int occupancy, const float* d_rgb,
+                          const float* d_acc, float* d_raw, void* stream);
+int mpsnerf_gather_tokens_bwd(const float* uv, int64_t count, int n_views, const mpsnerf_frame* frame,
+                              const float* d_tokens, int32_t ld, float* d_latent, void* stream);
+int mpsnerf_rows4_gather(const float* src, const int32_t* act_pid, int64_t count, float* dst, void* stream);
+int mpsnerf_rows4_scatter(const float* src, const int32_t* act_pid, int64_t count, float* dst, void* stream);
+
 /* bf16 tensor-core variant (tcgen05 / TMEM / bulk-async weight streaming).  `packed` is the
  * blob produced by mpsnerf_b200.engine.pack_weights_bf16 (layout: DESIGN.md section 5). */
 size_t mpsnerf_dense_bf16_workspace(int64_t count, int n_views);

@@ -65,6 +65,14 @@ SIGNATURES = {
     "mpsnerf_dense_fp32_workspace": (c_size_t, [c_int64, c_int]),
     "mpsnerf_dense_fp32": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_dense_train_workspace": (c_size_t, [c_int64, c_int]),
+    "mpsnerf_dense_train_fwd": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_dense_train_bwd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_composite_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_gather_tokens_bwd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "mpsnerf_rows4_gather": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mpsnerf_rows4_scatter": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "mpsnerf_dense_bf16_workspace": (c_size_t, [c_int64, c_int]),
     "mpsnerf_dense_bf16": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p,
                                    c_int64, c_void_p, c_void_p, c_void_p]),

@@ -198,12 +198,13 @@ class RenderEngine:
 
     # ------------------------------------------------------------------ per-frame preparation
     @torch.no_grad()
-    def prepare_frame(self, sp, tp, smpl):
-        """sp/tp: squeezed input dicts on the CUDA device; smpl: CPU tensor dict of the gender."""
+    def prepare_frame(self, sp, tp, smpl, trunk=True):
+        """sp/tp: squeezed input dicts on the CUDA device; smpl: CPU tensor dict of the gender.
+        ``trunk=False`` skips the encoder branch (the training step runs the trunk under autograd itself)."""
         with self.span("prep"):
-            return self._prepare_frame(sp, tp, smpl)
+            return self._prepare_frame(sp, tp, smpl, trunk)
 
-    def _prepare_frame(self, sp, tp, smpl):
+    def _prepare_frame(self, sp, tp, smpl, trunk=True):
         """~45 small launches (trunk, layout changes, K0, two grid builds) whose GPU time is ~0.45 ms but whose
         launch overhead is ~1 ms when issued one by one behind an idle GPU: they are captured once per
         (shape, device, weights) into THREE CUDA graphs over static input / output buffers -- front (frame header,
@@ -242,17 +243,18 @@ class RenderEngine:
                 self._prep_lbs(ins, ctx, sides[2])
                 ctx.ev_lbs = torch.cuda.Event()
                 ctx.ev_lbs.record()
-            with torch.cuda.stream(s_trunk):
-                self._prep_trunk(ins, ctx)
-                ctx._latent.record_stream(main)
-                ctx._img4.record_stream(main)
-                ctx.ev_trunk = torch.cuda.Event()
-                ctx.ev_trunk.record()
+            if trunk:
+                with torch.cuda.stream(s_trunk):
+                    self._prep_trunk(ins, ctx)
+                    ctx._latent.record_stream(main)
+                    ctx._img4.record_stream(main)
+                    ctx.ev_trunk = torch.cuda.Event()
+                    ctx.ev_trunk.record()
             _lib.count_launches(4)
             return ctx
         m = self.net.encoder_2d.model
-        key = (str(dev), self.precision, id(smpl), tuple(tuple(t.shape) for t in ins),
-               tuple(p._version for p in m.parameters()) + tuple(bf._version for bf in m.buffers()))
+        key = (str(dev), self.precision, id(smpl), tuple(tuple(t.shape) for t in ins), bool(trunk),
+               (tuple(p._version for p in m.parameters()) + tuple(bf._version for bf in m.buffers())) if trunk else ())
         g = self._prep_graphs.get(key)
         if g is None:
             try:
@@ -261,15 +263,16 @@ class RenderEngine:
                 ctx = self._new_ctx(static, smpl)
                 warm = torch.cuda.Stream(device=dev)
                 warm.wait_stream(main)
+                bodies = [lambda: self._prep_front(static, ctx), lambda: self._prep_lbs(static, ctx, sides[2])]
+                if trunk:               # (the training step runs the trunk itself, under autograd, in training mode)
+                    bodies.append(lambda: self._prep_trunk(static, ctx))
                 with torch.cuda.stream(warm):          # warm-up outside the capture (cuDNN plans, lazy inits)
-                    self._prep_front(static, ctx)
-                    self._prep_lbs(static, ctx, sides[2])
-                    self._prep_trunk(static, ctx)
+                    for body in bodies:
+                        body()
                 main.wait_stream(warm)
                 torch.cuda.synchronize(dev)
                 graphs = []
-                for body in (lambda: self._prep_front(static, ctx), lambda: self._prep_lbs(static, ctx, sides[2]),
-                             lambda: self._prep_trunk(static, ctx)):
+                for body in bodies:
                     gr = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gr):
                         body()
@@ -289,7 +292,7 @@ class RenderEngine:
                               "running it eagerly from now on (MPSNERF_PREP_GRAPH=0 silences this)")
                 self._use_prep_graph = False
                 torch.cuda.synchronize(dev)
-                return self._prepare_frame(sp, tp, smpl)
+                return self._prepare_frame(sp, tp, smpl, trunk)
         graphs, static, ctx = g
         torch._foreach_copy_(static, ins)
         # The side branches start BEHIND the front (default): its single-CTA grid build then runs alone (3x faster than
@@ -307,10 +310,11 @@ class RenderEngine:
             graphs[1].replay()
             ctx.ev_lbs = torch.cuda.Event()
             ctx.ev_lbs.record()
-        with torch.cuda.stream(s_trunk):
-            graphs[2].replay()
-            ctx.ev_trunk = torch.cuda.Event()
-            ctx.ev_trunk.record()
+        if trunk:
+            with torch.cuda.stream(s_trunk):
+                graphs[2].replay()
+                ctx.ev_trunk = torch.cuda.Event()
+                ctx.ev_trunk.record()
         _lib.count_launches(4)
         return ctx
 

@@ -142,6 +142,13 @@ class SKinningBatch(nn.Module):
             self._frame_key = self._frame_ctx = None      # a context belongs to the engine that prepared it
         return self._engine
 
+    def train_engine(self):
+        """State of the training path (fp32 engine + dense-gradient bucket), built on first use."""
+        if getattr(self, "_train_engine", None) is None:
+            from ..train import TrainEngine
+            self._train_engine = TrainEngine(self)
+        return self._train_engine
+
     def _smpl_for(self, gender):
         """SMPL tables of ``sp_input['gender']`` (1 male, 0 female, else neutral; :335-340).  The choice is made on the
         host (it selects table pointers), so a device-resident gender costs one device -> host read -- a full
@@ -195,8 +202,8 @@ class SKinningBatch(nn.Module):
 
     def forward(self, sp_input, tp_input, world_query_pts, viewdir=None):
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("training (backward) through the CUDA hot path is not built yet; "
-                                      "call under torch.no_grad() / eval()")
+            raise NotImplementedError("network_fn(points) has no backward: train through run_nerf_batch.render() "
+                                      "(mpsnerf_b200.train), or call under torch.no_grad() / eval()")
         pts = world_query_pts.reshape(-1, 3).float().contiguous()
         sp, tp = sequeeze_0(sp_input, tp_input) if sp_input["img_all"].dim() == 5 else (sp_input, tp_input)
         ctx = self.frame_context(sp, tp)

@@ -112,7 +112,16 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, pert
     """
     net = _net_of(network_fn)
     if net.training and torch.is_grad_enabled():
-        raise NotImplementedError("training through the CUDA hot path is not built yet")
+        # training step (BASELINE config 4): forward with saved intermediates + hand-written backward, train.py
+        if global_args.smooth_loss and sp_input is not None and "smooth_interval" in sp_input and "global_step" in sp_input \
+                and int(sp_input["global_step"].reshape(-1)[0]) % int(sp_input["smooth_interval"].reshape(-1)[0]) == 0:
+            raise NotImplementedError("smooth-loss step (normals by double backward, ref :60-79) is not built: "
+                                      "train with --smooth_loss 0 or skip the interval steps")
+        from .train import render_rays_train
+        if _rays_ready is not None:
+            torch.cuda.current_stream(ray_batch.device).wait_event(_rays_ready)
+        return render_rays_train(net, ray_batch, sp_input, tp_input, N_samples, perturb, perturb_u, white_bkgd,
+                                 bool(global_args.occupancy), _select)
     B, C = ray_batch.shape[:2]
     dev = ray_batch.device
     S = int(N_samples)

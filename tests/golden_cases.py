@@ -50,3 +50,23 @@ def build_case(spec):
     else:
         sp, tp = synthetic.batch_scenes(scenes)
     return scenes, sd, sp, tp
+
+
+# ---- training step (BASELINE config 4): one subject, rays with stratified jitter, a seeded target image
+TRAIN_CASE = dict(scene=dict(kind="thuman", seed=11, H=128, W=128, novel_pose=True), n_rays=320, S=48, alpha_gain=300.0,
+                  alpha_bias=2.0)
+
+
+def build_train_case():
+    """-> (scene, state_dict, ray ids, S, u (n_rays, S), target rgb (n_rays, 3), bkgd_msk (n_rays,))."""
+    import numpy as np
+    from mpsnerf_b200 import synthetic
+    spec = TRAIN_CASE
+    scene = synthetic.make_scene(**spec["scene"])
+    sd = synthetic.seeded_state_dict(scene.seed, spec["alpha_gain"], spec["alpha_bias"])
+    ids = synthetic.inbox_ray_subset(scene, spec["n_rays"])
+    rng = np.random.RandomState(1234)
+    u = rng.uniform(0, 1, (spec["n_rays"], spec["S"])).astype(np.float32)
+    target = rng.uniform(0, 1, (spec["n_rays"], 3)).astype(np.float32)
+    msk = (rng.uniform(0, 1, spec["n_rays"]) > 0.5).astype(np.float32)
+    return scene, sd, ids, spec["S"], u, target, msk

@@ -99,3 +99,66 @@ def test_sharded_render_two_ranks_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert sorted(out.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mpsnerf_b200.engine import DENSE_FP32_ORDER
+    from mpsnerf_b200.train import DenseBucket, TrainStep
+
+    class Tiny(torch.nn.Module):          # parameters with the names / shapes the bucket walks, nothing else
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(0)
+            self._names = {}
+            for i, k in enumerate(DENSE_FP32_ORDER):
+                p = torch.nn.Parameter(torch.randn(3 + i % 5, 2 + i % 3, generator=g))
+                self.register_parameter("p%d" % i, p)
+                self._names[k] = p
+            self.encoder_2d = torch.nn.Linear(4, 3)
+
+        def named_parameters(self, *a, **k):
+            return list(self._names.items()) + [("encoder_2d." + n, p) for n, p in self.encoder_2d.named_parameters()]
+
+    net = Tiny()
+    b = DenseBucket(net)
+    assert len(b.params) == 46 and b.flat.numel() % 64 == 0
+    b.begin_step(world)
+    b.pending = 2                          # two render nodes in this step
+    for v in b.views:                      # what the backward kernels do: accumulate into the views
+        v += float(rank + 1)
+    b.node_done()
+    assert b.work is None                  # the all-reduce waits for the last node
+    for v in b.views:
+        v += 10.0 * (rank + 1)
+    b.node_done()
+    assert b.work is not None
+    b.finish()
+    want = sum(11.0 * (r + 1) for r in range(world)) / world
+    for p in b.params:
+        assert p.grad is not None and torch.allclose(p.grad, torch.full_like(p, want))
+    # trunk gradients: one flat all-reduce, averaged
+    ts = TrainStep(net, optimizer=None)
+    for p in net.encoder_2d.parameters():
+        p.grad = torch.full_like(p, float(rank))
+    ts.allreduce_trunk(world)
+    for p in net.encoder_2d.parameters():
+        assert torch.allclose(p.grad, torch.full_like(p, sum(range(world)) / world))
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put(rank)
+
+
+def test_gradient_bucket_allreduce_two_ranks_gloo():
+    """DenseBucket / TrainStep.allreduce_trunk (the data-parallel plumbing of the training step) on two gloo ranks."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert sorted(out.get(timeout=5) for _ in range(2)) == [0, 1]
