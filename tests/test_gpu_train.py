@@ -41,8 +41,9 @@ def test_composite_backward_against_autograd(S, occupancy):
     rays8 = torch.zeros(N, 8)
     rays8[:, 3:6] = d
     got = torch.empty(N, S, 4, device="cuda")
-    _lib.check(lib.mpsnerf_composite_bwd(_lib.ptr(raw.cuda()), _lib.ptr(rays8.cuda()), N, S, None, None, _lib.ptr(z.cuda()),
-                                         occupancy, _lib.ptr(d_rgb.cuda()), _lib.ptr(d_acc.cuda()), _lib.ptr(got), None), "composite_bwd")
+    raw_d, rays_d, z_d, drgb_d, dacc_d = raw.cuda(), rays8.cuda(), z.cuda(), d_rgb.cuda(), d_acc.cuda()     # (kept alive)
+    _lib.check(lib.mpsnerf_composite_bwd(_lib.ptr(raw_d), _lib.ptr(rays_d), N, S, None, None, _lib.ptr(z_d),
+                                         occupancy, _lib.ptr(drgb_d), _lib.ptr(dacc_d), _lib.ptr(got), None), "composite_bwd")
     torch.cuda.synchronize()
     scale = float(want.abs().max())
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), atol=2e-5 * max(scale, 1.0), rtol=2e-4)
@@ -65,7 +66,8 @@ def test_gather_backward_against_autograd():
     frame = torch.frombuffer(bytearray(bytes(fr)), dtype=torch.uint8).cuda()
     got = torch.zeros(V, Hf, Wf, 128, device="cuda")
     uv_d = uv.transpose(0, 1).contiguous().cuda()                                             # (n, V, 2)
-    _lib.check(lib.mpsnerf_gather_tokens_bwd(_lib.ptr(uv_d), n, V, _lib.ptr(frame), _lib.ptr(d_tok.cuda()), 155, _lib.ptr(got), None),
+    dtok_d = d_tok.cuda()
+    _lib.check(lib.mpsnerf_gather_tokens_bwd(_lib.ptr(uv_d), n, V, _lib.ptr(frame), _lib.ptr(dtok_d), 155, _lib.ptr(got), None),
                "gather_tokens_bwd")
     torch.cuda.synchronize()
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), atol=2e-4, rtol=1e-4)
@@ -100,7 +102,8 @@ def test_dense_train_forward_backward_against_autograd(V, n):
     tok_d, xc_d = tok.cuda(), xc.cuda()
     _lib.check(lib.mpsnerf_dense_train_fwd(_lib.ptr(tok_d), 155, _lib.ptr(xc_d), n, V, wt, _lib.ptr(out4), _lib.ptr(ws), None), "fwd")
     d_tok = torch.empty(n, V, 155, device="cuda")
-    _lib.check(lib.mpsnerf_dense_train_bwd(_lib.ptr(d_out.cuda()), n, V, wt, gt, _lib.ptr(d_tok), _lib.ptr(ws), None), "bwd")
+    dout_d = d_out.cuda()
+    _lib.check(lib.mpsnerf_dense_train_bwd(_lib.ptr(dout_d), n, V, wt, gt, _lib.ptr(d_tok), _lib.ptr(ws), None), "bwd")
     torch.cuda.synchronize()
     scale = float(out_ref.abs().max())
     np.testing.assert_allclose(out4.cpu().numpy(), out_ref.detach().numpy(), atol=2e-4 * max(1.0, scale))
@@ -110,11 +113,21 @@ def test_dense_train_forward_backward_against_autograd(V, n):
         err = float((got.cpu() - want).abs().max()) / max(float(want.abs().max()), 1e-20)
         assert err <= 2e-3, (k, err)        # fp32 sums over the points in a different order (atomics, tiles)
     # gradients accumulate: a second backward doubles them
-    _lib.check(lib.mpsnerf_dense_train_bwd(_lib.ptr(d_out.cuda()), n, V, wt, gt, _lib.ptr(d_tok), _lib.ptr(ws), None), "bwd")
+    _lib.check(lib.mpsnerf_dense_train_bwd(_lib.ptr(dout_d), n, V, wt, gt, _lib.ptr(d_tok), _lib.ptr(ws), None), "bwd")
     torch.cuda.synchronize()
     k0 = DENSE_FP32_ORDER.index("pts_linears.3.weight")
     np.testing.assert_allclose(g_dev[k0].cpu().numpy(), 2 * par["pts_linears.3.weight"].grad.numpy(),
                                atol=4e-3 * float(par["pts_linears.3.weight"].grad.abs().max()))
+
+
+@pytest.fixture
+def strict_fp32_convs():
+    """cuDNN convolutions default to TF32 (forward and backward); the reference gradients were produced on CPU in
+    fp32, so the trunk runs in true fp32 for the comparison."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
 
 
 def _train_setup():
@@ -131,7 +144,7 @@ def _train_setup():
     return R, net, handle, kw, torch.from_numpy(target)[None].cuda(), torch.from_numpy(msk)[None, :, None].cuda()
 
 
-def test_training_step_gradients_against_reference_autograd():
+def test_training_step_gradients_against_reference_autograd(strict_fp32_convs):
     """render() in training mode + loss.backward(): every live parameter's gradient against what the UNMODIFIED
     reference's autograd produced for the same step (and the forward outputs against its render)."""
     from test_train_oracle import GOLD, check_grads_against_golden
@@ -162,12 +175,13 @@ def test_train_step_optimises():
     """TrainStep on one fixed batch: Adam steps through the CUDA path reduce the loss, parameters and BN statistics move."""
     from mpsnerf_b200.train import TrainStep
     R, net, handle, kw, target, msk = _train_setup()
-    opt = torch.optim.Adam([p for p in net.parameters()], lr=5e-4, betas=(0.9, 0.999))
+    # (the seeded weights have a density head of gain 300: a small step size keeps the descent monotone)
+    opt = torch.optim.Adam([p for p in net.parameters()], lr=2e-5, betas=(0.9, 0.999))
     ts = TrainStep(handle, opt, acc_loss=True)
     w0 = net.pts_linears[3].weight.detach().clone()
     rm0 = net.encoder_2d.model.bn1.running_mean.clone()
     losses = [float(ts.step(R.render, target_rgb=target, bkgd_msk=msk, **kw)) for _ in range(8)]
-    assert losses[-1] < losses[0] and all(np.isfinite(losses))
+    assert losses[-1] < losses[0] and all(np.isfinite(losses)), losses
     assert not torch.equal(w0, net.pts_linears[3].weight.detach())
     assert not torch.equal(rm0, net.encoder_2d.model.bn1.running_mean)
     # back to inference: eval() + no_grad goes through the production path again
