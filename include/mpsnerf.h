@@ -259,6 +259,28 @@ int mpsnerf_mlp_bf16_dc(const void* tokens, const float* xc, int64_t first, int6
                         const int32_t* count_dev, int n_views, const void* packed, size_t packed_bytes,
                         const int32_t* act_pid, float* raw, void* workspace, void* stream);
 
+/* ---- fused render_rays: the whole per-ray path of a frame in ONE call ------------------------------------------
+ * Replaces render_rays (run_nerf_batch.py:401-444: sampling -> network_query_fn -> raw2outputs) for the tensor-core
+ * path: enqueues K1, K3, K4, T, M and K6 on `stream`, every stage reading the active count on the device.
+ * Inputs: rays (n_rays, 8), t_vals (S), u (n_rays, S) or NULL; the prepared frame state (frame, the two grids, skin_w,
+ * NHWC latent, img4) and the packed weights.  Outputs: the per-sample extras (raw, pts_mask, smpl_query, smpl_src; P =
+ * n_rays * S rows), the per-ray maps (rgb, disp, acc, depth; depth may be NULL) and *act_count (device) = the number
+ * of active points.  `capacity` = active points the workspace holds; points beyond it are NOT evaluated -- the caller
+ * compares *act_count with capacity afterwards and, if it was exceeded, runs the remainder through the staged entry
+ * points (active list: mpsnerf_render_rays_active_list) and mpsnerf_composite again.  event_lbs / event_trunk:
+ * optional cudaEvent_t the stream waits on before K3 / K4 (the frame preparation may run on other streams).
+ * No allocation, no synchronisation; workspace >= mpsnerf_render_rays_workspace(...) bytes, 256-byte aligned. */
+size_t mpsnerf_render_rays_workspace(int64_t n_rays, int32_t S, int n_views, int64_t capacity);
+int mpsnerf_render_rays_bf16(const float* rays, int64_t n_rays, int32_t S, const float* t_vals, const float* u,
+                             const mpsnerf_frame* frame, const void* grid_tp, const void* grid_tv,
+                             const float* skin_w, const float* latent, const float* img4, const void* packed,
+                             size_t packed_bytes, int n_views, int occupancy, float* raw, float* pts_mask,
+                             float* smpl_query, float* smpl_src, float* rgb, float* disp, float* acc, float* depth,
+                             int32_t* act_count, int64_t capacity, void* workspace, size_t workspace_bytes,
+                             void* event_lbs, void* event_trunk, void* stream);
+int mpsnerf_render_rays_active_list(void* workspace, int64_t n_rays, int32_t S, int n_views, int64_t capacity,
+                                    int32_t** act_pid, int32_t** act_idx2, float** act_q);
+
 /* ---- K6: alpha compositing --------------------------------------------------------------
  * Replaces raw2outputs (run_nerf_batch.py:369-398).  One warp per ray.
  *   raw (n_rays,S,4); z is regenerated from rays/t_vals/u exactly as in K1, or read from

@@ -80,6 +80,11 @@ SIGNATURES = {
                                    c_int64, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_mlp_bf16": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p,
                                    c_int64, c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_render_rays_workspace": (c_size_t, [c_int64, c_int32, c_int, c_int64]),
+    "mpsnerf_render_rays_bf16": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int] + [c_void_p] * 9 +
+                                 [c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "mpsnerf_render_rays_active_list": (c_int, [c_void_p, c_int64, c_int32, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_composite": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpsnerf_b200.so")
 SOURCES = ["abi.cu", "raygen.cu", "frame_prep.cu", "grid_build.cu", "sample_knn.cu", "deform.cu", "gather.cu", "composite.cu", "occupancy.cu",
-           "dense_fp32.cu", "train_bwd.cu", "dense_tc.cu"]
+           "dense_fp32.cu", "train_bwd.cu", "render_rays.cu", "dense_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 

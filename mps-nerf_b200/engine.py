@@ -101,10 +101,13 @@ class RenderEngine:
         self._ws = {}
         self._packed = None
         self._packed_key = None
+        self._dense_params = None
+        self._trunk_params = None
         self._smpl_cache = {}
         self._trunk = None
         self._pinned = {}
         self._use_device_count = os.environ.get("MPSNERF_DEVICE_COUNT", "1") != "0"
+        self._use_fused = os.environ.get("MPSNERF_FUSED_CALL", "1") != "0"
         self._side = {}
         self._prep_graphs = {}
         self._use_prep_graph = os.environ.get("MPSNERF_PREP_GRAPH", "1") != "0"
@@ -167,7 +170,7 @@ class RenderEngine:
               and all(type(b).__name__ == "BasicBlock" and b.downsample is None for b in m.layer1))
         if not ok:
             return enc(img)
-        key = tuple(p._version for p in m.parameters()) + tuple(b._version for b in m.buffers())
+        key = tuple(t._version for t in self._trunk_state())
         if self._trunk is None or self._trunk[0] != key or self._trunk[1][0][0].device != img.device:
             def fold(conv, bn):
                 scale = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
@@ -254,7 +257,7 @@ class RenderEngine:
             return ctx
         m = self.net.encoder_2d.model
         key = (str(dev), self.precision, id(smpl), tuple(tuple(t.shape) for t in ins), bool(trunk),
-               (tuple(p._version for p in m.parameters()) + tuple(bf._version for bf in m.buffers())) if trunk else ())
+               tuple(t._version for t in self._trunk_state()) if trunk else ())
         g = self._prep_graphs.get(key)
         if g is None:
             try:
@@ -404,12 +407,45 @@ class RenderEngine:
                            acc_map=torch.empty(N, device=dev), depth_map=torch.empty(N, device=dev))
             out["n_active"] = 0
             return out
-        act_pid = self._buf("act_pid", 4 * P, dev).view(torch.int32)
-        act_idx2 = self._buf("act_idx2", 4 * P, dev).view(torch.int32)
-        act_q = self._buf("act_q", 12 * P, dev).view(torch.float32)
         counter = self._buf("counter", 256, dev).view(torch.int32)
         device_count = False
-        if all_active:      # extract_mesh: every point is evaluated, canonical = the point itself
+        k6_done = False
+        # One C call for the whole frame (mpsnerf_render_rays_bf16: K1, K3, K4, T, M, K6 with the active count read on
+        # the device) whenever nothing needs the stages one by one (per-stage timers, debug captures, direct point
+        # queries); MPSNERF_FUSED_CALL=0 keeps the staged calls.
+        fused = (self.precision == "bf16" and self.debug is None and self.timers is None and self._use_device_count
+                 and self._use_fused and composite and points is None and not all_active)
+        if fused:
+            cap = int(min(self.slab, P))
+            wsb = lib.mpsnerf_render_rays_workspace(N, S, V, cap)
+            ws_all = self._buf("render_ws", wsb, dev)
+            a4 = (4 * P + 255) // 256 * 256              # layout of the workspace head: act_pid | act_idx2 | act_q
+            act_pid = ws_all[:4 * P].view(torch.int32)
+            act_idx2 = ws_all[a4:a4 + 4 * P].view(torch.int32)
+            act_q = ws_all[2 * a4:2 * a4 + 12 * P].view(torch.float32)
+            out.update(rgb_map=torch.empty(N, 3, device=dev), disp_map=torch.empty(N, device=dev),
+                       acc_map=torch.empty(N, device=dev), depth_map=torch.empty(N, device=dev))
+            packed = self._packed_weights(dev)
+            ev = lambda e: None if e is None else ctypes.c_void_p(e.cuda_event)
+            _lib.check(lib.mpsnerf_render_rays_bf16(
+                _lib.ptr(rays8), N, S, _lib.ptr(t_vals), _lib.ptr(u), _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.grid_tp),
+                _lib.ptr(ctx.grid_tv), _lib.ptr(ctx.skin_w), _lib.ptr(ctx._latent), _lib.ptr(ctx._img4), _lib.ptr(packed),
+                packed.numel(), V, 1 if occupancy else 0, _lib.ptr(raw), _lib.ptr(mask), _lib.ptr(sq), _lib.ptr(ss),
+                _lib.ptr(out["rgb_map"]), _lib.ptr(out["disp_map"]), _lib.ptr(out["acc_map"]), _lib.ptr(out["depth_map"]),
+                _lib.ptr(counter), cap, _lib.ptr(ws_all), wsb, ev(ctx.ev_lbs), ev(ctx.ev_trunk), _stream()), "render_rays_bf16")
+            _lib.count_launches(6)
+            pinned = self._pinned_count(dev)
+            pinned.copy_(counter[:1], non_blocking=True)
+            count_event = torch.cuda.Event()
+            count_event.record()
+            device_count, k6_done, done_upto = True, True, cap
+        else:
+            act_pid = self._buf("act_pid", 4 * P, dev).view(torch.int32)
+            act_idx2 = self._buf("act_idx2", 4 * P, dev).view(torch.int32)
+            act_q = self._buf("act_q", 12 * P, dev).view(torch.float32)
+        if fused:
+            pass
+        elif all_active:      # extract_mesh: every point is evaluated, canonical = the point itself
             act_pid[:P] = torch.arange(P, device=dev, dtype=torch.int32)
             act_q[:3 * P] = points.reshape(-1)
             mask.fill_(1.0)
@@ -440,7 +476,6 @@ class RenderEngine:
             else:
                 n_act = int(counter[0].item())          # host-count path: the one host sync of the frame
                 done_upto = 0
-        k6_done = False
 
         def composite_now():
             if "rgb_map" not in out:
@@ -456,7 +491,7 @@ class RenderEngine:
         if not all_active and device_count:
             # K6 goes into the queue BEFORE the host looks at the count: the frame is then enqueued without a single
             # host wait, and the (rare) overflow beyond `cap` is handled afterwards -- remainder slabs, K6 once more
-            if composite and points is None:
+            if composite and points is None and not k6_done:
                 composite_now()
                 k6_done = True
             count_event.synchronize()
@@ -560,9 +595,25 @@ class RenderEngine:
             _lib.check(lib.mpsnerf_mlp_bf16_dc(*dense_args), "mlp_bf16_dc")
         _lib.count_launches(4)
 
+    def _live_dense(self):
+        """The 46 live tensors of the transformer + MLP (cached: walking all ~370 parameters of the network to
+        collect their versions cost 0.1 ms of host time per frame)."""
+        if self._dense_params is None:
+            named = dict(self.net.named_parameters())
+            self._dense_params = [named[k] for k in DENSE_FP32_ORDER]
+        return self._dense_params
+
+    def _trunk_state(self):
+        """Parameters and buffers of the live part of the encoder trunk (conv1, bn1, layer1)."""
+        if self._trunk_params is None:
+            m = self.net.encoder_2d.model
+            mods = [m.conv1, m.bn1, m.layer1]
+            self._trunk_params = [t for mod in mods for t in list(mod.parameters()) + list(mod.buffers())]
+        return self._trunk_params
+
     def _packed_weights(self, dev):
         from .pack import pack_weights_bf16
-        key = tuple(p._version for p in self.net.parameters())
+        key = tuple(p._version for p in self._live_dense())
         if self._packed is None or key != self._packed_key or self._packed.device != dev:
             self._packed = pack_weights_bf16(self.net, dev)
             self._packed_key = key

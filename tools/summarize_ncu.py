@@ -12,7 +12,7 @@ from collections import OrderedDict
 def short(name):
     name = name.replace("void ", "")
     for k in ("xformer_tc_kernel", "mlp_tc_kernel", "sample_knn_kernel", "deform_project_kernel", "gather_tokens_kernel",
-              "composite_kernel", "grid_build", "frame_prepare", "fused_tc_kernel"):
+              "composite_kernel", "grid_build", "frame_prep_kernel", "frame_header_kernel", "raygen_kernel", "fused_tc_kernel"):
         if k in name:
             return name[:name.index("(")] if "(" in name else name
     if "(" in name:
