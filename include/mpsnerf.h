@@ -269,6 +269,8 @@ int mpsnerf_mlp_bf16_dc(const void* tokens, const float* xc, int64_t first, int6
  * compares *act_count with capacity afterwards and, if it was exceeded, runs the remainder through the staged entry
  * points (active list: mpsnerf_render_rays_active_list) and mpsnerf_composite again.  event_lbs / event_trunk:
  * optional cudaEvent_t the stream waits on before K3 / K4 (the frame preparation may run on other streams).
+ * host_count (pinned host memory) / event_count (cudaEvent_t), both optional: the count is copied to the host and the
+ * event recorded right behind K1, so the caller can read it long before the frame has finished.
  * No allocation, no synchronisation; workspace >= mpsnerf_render_rays_workspace(...) bytes, 256-byte aligned. */
 size_t mpsnerf_render_rays_workspace(int64_t n_rays, int32_t S, int n_views, int64_t capacity);
 int mpsnerf_render_rays_bf16(const float* rays, int64_t n_rays, int32_t S, const float* t_vals, const float* u,
@@ -277,7 +279,8 @@ int mpsnerf_render_rays_bf16(const float* rays, int64_t n_rays, int32_t S, const
                              size_t packed_bytes, int n_views, int occupancy, float* raw, float* pts_mask,
                              float* smpl_query, float* smpl_src, float* rgb, float* disp, float* acc, float* depth,
                              int32_t* act_count, int64_t capacity, void* workspace, size_t workspace_bytes,
-                             void* event_lbs, void* event_trunk, void* stream);
+                             void* event_lbs, void* event_trunk, int32_t* host_count, void* event_count,
+                             void* stream);
 int mpsnerf_render_rays_active_list(void* workspace, int64_t n_rays, int32_t S, int n_views, int64_t capacity,
                                     int32_t** act_pid, int32_t** act_idx2, float** act_q);
 

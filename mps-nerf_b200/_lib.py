@@ -83,7 +83,7 @@ SIGNATURES = {
     "mpsnerf_render_rays_workspace": (c_size_t, [c_int64, c_int32, c_int, c_int64]),
     "mpsnerf_render_rays_bf16": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int] + [c_void_p] * 9 +
-                                 [c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+                                 [c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_render_rays_active_list": (c_int, [c_void_p, c_int64, c_int32, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "mpsnerf_composite": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

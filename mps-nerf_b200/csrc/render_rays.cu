@@ -44,7 +44,8 @@ extern "C" int mpsnerf_render_rays_bf16(const float* rays, int64_t n_rays, int32
                                         size_t packed_bytes, int n_views, int occupancy, float* raw, float* pts_mask,
                                         float* smpl_query, float* smpl_src, float* rgb, float* disp, float* acc, float* depth,
                                         int32_t* act_count, int64_t capacity, void* workspace, size_t workspace_bytes,
-                                        void* event_lbs, void* event_trunk, void* stream) {
+                                        void* event_lbs, void* event_trunk, int32_t* host_count, void* event_count,
+                                        void* stream) {
   MPS_REQUIRE(n_rays >= 0 && S >= 1 && capacity >= 1 && n_views >= 2 && n_views <= 4);
   const int64_t P = n_rays * S;
   if (P == 0) return MPSNERF_OK;
@@ -59,6 +60,9 @@ extern "C" int mpsnerf_render_rays_bf16(const float* rays, int64_t n_rays, int32
   int rc = mpsnerf_sample_knn(rays, n_rays, S, t_vals, u, nullptr, frame, grid_tp, raw, pts_mask, smpl_query, smpl_src, w.act_pid,
                               w.act_idx2, w.act_q, act_count, stream);
   if (rc != MPSNERF_OK) return rc;
+  // the count goes to the host right behind K1 (not behind the frame): the caller can look at it while T / M still run
+  if (host_count) MPS_CUDA(cudaMemcpyAsync(host_count, act_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (event_count) MPS_CUDA(cudaEventRecord((cudaEvent_t)event_count, st));
   // the LBS transform sets / template grid and the encoder latent may be produced on other streams (engine.py)
   if (event_lbs) MPS_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)event_lbs, 0));
   rc = mpsnerf_deform_project_dc(w.act_pid, w.act_idx2, w.act_q, 0, capacity, act_count, skin_w, frame, grid_tv, w.xc, w.uv,

@@ -106,6 +106,7 @@ class RenderEngine:
         self._smpl_cache = {}
         self._trunk = None
         self._pinned = {}
+        self._count_events = {}
         self._use_device_count = os.environ.get("MPSNERF_DEVICE_COUNT", "1") != "0"
         self._use_fused = os.environ.get("MPSNERF_FUSED_CALL", "1") != "0"
         self._side = {}
@@ -427,17 +428,16 @@ class RenderEngine:
                        acc_map=torch.empty(N, device=dev), depth_map=torch.empty(N, device=dev))
             packed = self._packed_weights(dev)
             ev = lambda e: None if e is None else ctypes.c_void_p(e.cuda_event)
+            pinned = self._pinned_count(dev)
+            count_event = self._count_event(dev)
             _lib.check(lib.mpsnerf_render_rays_bf16(
                 _lib.ptr(rays8), N, S, _lib.ptr(t_vals), _lib.ptr(u), _lib.ptr(ctx.frame_dev), _lib.ptr(ctx.grid_tp),
                 _lib.ptr(ctx.grid_tv), _lib.ptr(ctx.skin_w), _lib.ptr(ctx._latent), _lib.ptr(ctx._img4), _lib.ptr(packed),
                 packed.numel(), V, 1 if occupancy else 0, _lib.ptr(raw), _lib.ptr(mask), _lib.ptr(sq), _lib.ptr(ss),
                 _lib.ptr(out["rgb_map"]), _lib.ptr(out["disp_map"]), _lib.ptr(out["acc_map"]), _lib.ptr(out["depth_map"]),
-                _lib.ptr(counter), cap, _lib.ptr(ws_all), wsb, ev(ctx.ev_lbs), ev(ctx.ev_trunk), _stream()), "render_rays_bf16")
+                _lib.ptr(counter), cap, _lib.ptr(ws_all), wsb, ev(ctx.ev_lbs), ev(ctx.ev_trunk),
+                ctypes.c_void_p(pinned.data_ptr()), ev(count_event), _stream()), "render_rays_bf16")
             _lib.count_launches(6)
-            pinned = self._pinned_count(dev)
-            pinned.copy_(counter[:1], non_blocking=True)
-            count_event = torch.cuda.Event()
-            count_event.record()
             device_count, k6_done, done_upto = True, True, cap
         else:
             act_pid = self._buf("act_pid", 4 * P, dev).view(torch.int32)
@@ -561,6 +561,15 @@ class RenderEngine:
         if composite and points is None and (n_act > done_upto or not k6_done):
             composite_now()
         return out
+
+    def _count_event(self, dev):
+        """A (re-recordable) event per device for "the active count has reached the host"; recorded once here so that
+        its CUDA handle exists before the C entry point records it."""
+        e = self._count_events.get(dev)
+        if e is None:
+            e = self._count_events[dev] = torch.cuda.Event()
+            e.record(torch.cuda.current_stream(dev))
+        return e
 
     def _pinned_count(self, dev):
         t = self._pinned.get(dev)
