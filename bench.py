@@ -84,7 +84,8 @@ def workload_config(workload, world, strong):
             "extras": "full reference contract (raw, pts_mask, smpl_query_pts, smpl_src_pts)",
             "includes": "per-frame prep + encoder trunk + K1..K6", "l2": "flushed in front of every timed step (512 MiB fill, outside the step's event pair)",
             "parallelism": (f"ONE target view dealt out to {world} GPUs in interleaved groups of 2 image rows, rays generated "
-                            f"on each GPU from the camera; no data-path collective" if strong
+                            f"on each GPU from the camera; encoder trunk split by latent rows + one NVLink all-gather of the "
+                            f"latent per frame (the path's only collective)" if strong
                             else f"one target view per GPU x{world}")}
 
 
@@ -152,6 +153,8 @@ def run_ours(a):
     _lib.check(_lib.load().mpsnerf_check_device(local), "check_device")
     scene, net, args = build_scene_and_net(a.precision, None if (strong or world == 1) else 1 + rank, workload)
     handle = R.NetworkHandle(net).to(dev).eval()
+    if strong and world > 1 and os.environ.get("MPSNERF_TRUNK_SHARD", "1") != "0":
+        net.engine().set_trunk_shard(rank, world)        # each rank encodes 1/N of the latent rows, NVLink all-gather
     H, W = scene.H, scene.W
     n_total = H * W
     Kc, Rc, Tc = scene.cams[scene.target]
@@ -259,6 +262,8 @@ def run_ours(a):
     # denominator a reader needs next to the N-GPU value (the driver's own N = 1 line is another workload)
     single = None
     if strong and world > 1:
+        sharded = net.engine().trunk_shard
+        net.engine().set_trunk_shard(None)                   # the one-GPU reference run cannot wait for the other ranks
         if rank == 0:
             r8, _ = gen_rays8(H, W, Kc, Rc, Tc, scene.bounds, device=dev)
             full = dict(rays=torch.stack([r8[:, 0:3], r8[:, 3:6]])[None].contiguous(), near=r8[None, :, 6:7].contiguous(),
@@ -268,6 +273,8 @@ def run_ours(a):
                       "what": "the whole frame on rank 0 alone, same run, resident inputs"}
             del full, r8
         barrier()
+        if sharded is not None:
+            net.engine().set_trunk_shard(*sharded)
     # load balance of the split: active points per rank
     act = torch.tensor([float(n_active)], device=dev, dtype=torch.float64)
     acts = [act.clone() for _ in range(world)]

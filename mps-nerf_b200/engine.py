@@ -58,6 +58,25 @@ def pack_kmajor_sw128(w, n_pad=None, k_pad=None):
     return t.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)
 
 
+_ROW_INDEX = {}
+
+
+def assemble_latent_rows(gathered, Hf):
+    """(world, V, mr, Wf, C) bands of latent rows, rank-major and padded to mr = ceil(Hf / world) rows each
+    (parallel.ray_block split) -> (V, Hf, Wf, C)."""
+    from .parallel import ray_block
+    world, V, mr, Wf, C = gathered.shape
+    x = gathered.permute(1, 0, 2, 3, 4).reshape(V, world * mr, Wf, C)
+    if Hf == world * mr:
+        return x.contiguous()
+    key = (Hf, world, str(gathered.device))
+    idx = _ROW_INDEX.get(key)
+    if idx is None:
+        idx = torch.cat([torch.arange(r * mr, r * mr + (e - s)) for r in range(world) for s, e in [ray_block(Hf, r, world)]])
+        idx = _ROW_INDEX[key] = idx.to(gathered.device)
+    return x.index_select(1, idx)
+
+
 class FrameContext:
     """Device-resident state of one (source, target) pair.
 
@@ -107,6 +126,7 @@ class RenderEngine:
         self._trunk = None
         self._pinned = {}
         self._count_events = {}
+        self.trunk_shard = None
         self._use_device_count = os.environ.get("MPSNERF_DEVICE_COUNT", "1") != "0"
         self._use_fused = os.environ.get("MPSNERF_FUSED_CALL", "1") != "0"
         self._side = {}
@@ -158,21 +178,18 @@ class RenderEngine:
         return tab
 
     # ------------------------------------------------------------------ encoder trunk (boundary: cuDNN)
-    @torch.no_grad()
-    def _encode(self, img):
-        """SpatialEncoder.forward (lib/encoder.py:256-306) for the shipped trunk shape (num_layers = 2, no first
-        pool, feature_scale = 0.5, eval mode), with BatchNorm folded into the convolutions and cuDNN's fused
-        conv+bias+ReLU / conv+bias+add+ReLU kernels: ~9 launches instead of ~35.  Any other trunk configuration
-        falls back to the module itself.  The folded weights are cached per parameter version."""
+    def _trunk_ok(self, img):
         enc = self.net.encoder_2d
         m = enc.model
-        ok = (enc.num_layers == 2 and not enc.use_first_pool and enc.feature_scale == 0.5 and not m.training
-              and img.shape[-1] % 2 == 0 and img.shape[-2] % 2 == 0
-              and all(type(b).__name__ == "BasicBlock" and b.downsample is None for b in m.layer1))
-        if not ok:
-            return enc(img)
+        return (enc.num_layers == 2 and not enc.use_first_pool and enc.feature_scale == 0.5 and not m.training
+                and img.shape[-1] % 2 == 0 and img.shape[-2] % 2 == 0
+                and all(type(b).__name__ == "BasicBlock" and b.downsample is None for b in m.layer1))
+
+    def _folded_trunk(self, dev):
+        """conv1 + layer1 with BatchNorm folded in (eval mode), channels_last, cached per parameter version."""
+        m = self.net.encoder_2d.model
         key = tuple(t._version for t in self._trunk_state())
-        if self._trunk is None or self._trunk[0] != key or self._trunk[1][0][0].device != img.device:
+        if self._trunk is None or self._trunk[0] != key or self._trunk[1][0][0].device != dev:
             def fold(conv, bn):
                 scale = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
                 w = (conv.weight.double() * scale[:, None, None, None]).float().contiguous(memory_format=torch.channels_last)
@@ -180,17 +197,67 @@ class RenderEngine:
                 return w, b
             layers = [fold(m.conv1, m.bn1)] + [f for blk in m.layer1 for f in (fold(blk.conv1, blk.bn1), fold(blk.conv2, blk.bn2))]
             self._trunk = (key, layers)
-        L = self._trunk[1]
-        # channels_last end to end: cuDNN's TF32 kernels are NHWC, and the NHWC view the gather wants is then free
-        x = F.avg_pool2d(img.float(), 2).contiguous(memory_format=torch.channels_last)   # == area interpolation at scale 0.5 for even sizes
+        return self._trunk[1]
+
+    @staticmethod
+    def _trunk_convs(x, L, nblocks):
+        """half-resolution image (channels_last) -> (conv1 output, layer1 output)"""
         x = torch.cudnn_convolution_relu(x, L[0][0], L[0][1], (2, 2), (3, 3), (1, 1), 1)
         lat0 = x
-        for i in range(len(m.layer1)):
+        for i in range(nblocks):
             w1, b1 = L[1 + 2 * i]
             w2, b2 = L[2 + 2 * i]
             y = torch.cudnn_convolution_relu(x, w1, b1, (1, 1), (1, 1), (1, 1), 1)
             x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, (1, 1), (1, 1), (1, 1), 1)
+        return lat0, x
+
+    @torch.no_grad()
+    def _encode(self, img):
+        """SpatialEncoder.forward (lib/encoder.py:256-306) for the shipped trunk shape (num_layers = 2, no first
+        pool, feature_scale = 0.5, eval mode), with BatchNorm folded into the convolutions and cuDNN's fused
+        conv+bias+ReLU / conv+bias+add+ReLU kernels: ~9 launches instead of ~35.  Any other trunk configuration
+        falls back to the module itself.  The folded weights are cached per parameter version."""
+        if not self._trunk_ok(img):
+            return self.net.encoder_2d(img)
+        L = self._folded_trunk(img.device)
+        # channels_last end to end: cuDNN's TF32 kernels are NHWC, and the NHWC view the gather wants is then free
+        x = F.avg_pool2d(img.float(), 2).contiguous(memory_format=torch.channels_last)   # == area interpolation at scale 0.5 for even sizes
+        lat0, x = self._trunk_convs(x, L, len(self.net.encoder_2d.model.layer1))
         return torch.cat([lat0, x], dim=1)
+
+    @torch.no_grad()
+    def _encode_rows(self, img, a, b):
+        """Latent rows [a, b) only (NCHW, (V, 128, b - a, Wf)): the trunk on a horizontal band of the images.
+
+        One frame split over N GPUs replicates the per-frame preparation; the trunk is its only large piece (0.6 ms of a
+        2.6 ms frame at 3 x 1000 x 1000 on 8 GPUs), so each rank computes 1/N of the latent rows and the bands are
+        all-gathered over NVLink (_prep_trunk_sharded).  A latent row depends on a finite band of input rows: conv1
+        (7 x 7, stride 2, pad 3) output row y reads half-resolution rows 2y - 3 .. 2y + 3, and each of the six 3 x 3
+        convolutions of layer1 widens the dependency by one latent row -- so the band is computed with a 6-row halo on
+        each interior side (zero padding is only right at the true image border; at a cut it corrupts one more row per
+        convolution, exactly the halo, which is cropped).  Same kernels and weights as _encode; results differ from the
+        unsplit trunk only by cuDNN's choice of tiling per size (TF32 / fp32 re-association, ~1e-6)."""
+        L = self._folded_trunk(img.device)
+        nblk = len(self.net.encoder_2d.model.layer1)
+        H = img.shape[-2]
+        Hh = H // 2
+        Hf = (Hh - 1) // 2 + 1
+        halo = 2 * nblk
+        la, lb = max(0, a - halo), min(Hf, b + halo)               # conv1 rows needed, incl. the layer1 halo
+        r0 = max(0, 2 * la - 4)                                     # even: keeps the stride-2 phase of conv1
+        r1 = min(Hh, 2 * (lb - 1) + 3 + 1)
+        x = F.avg_pool2d(img[:, :, 2 * r0:2 * r1].float(), 2).contiguous(memory_format=torch.channels_last)
+        x = torch.cudnn_convolution_relu(x, L[0][0], L[0][1], (2, 2), (3, 3), (1, 1), 1)
+        off = la - r0 // 2                                          # absolute conv1 row of x[..., j, :] is r0 / 2 + j
+        x = x[:, :, off:off + (lb - la)]
+        lat0 = x
+        for i in range(nblk):
+            w1, b1 = L[1 + 2 * i]
+            w2, b2 = L[2 + 2 * i]
+            y = torch.cudnn_convolution_relu(x, w1, b1, (1, 1), (1, 1), (1, 1), 1)
+            x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, (1, 1), (1, 1), (1, 1), 1)
+        sl = slice(a - la, a - la + (b - a))
+        return torch.cat([lat0[:, :, sl], x[:, :, sl]], dim=1)
 
     def _weights_fp32(self):
         sd = dict(self.net.named_parameters())
@@ -249,7 +316,7 @@ class RenderEngine:
                 ctx.ev_lbs.record()
             if trunk:
                 with torch.cuda.stream(s_trunk):
-                    self._prep_trunk(ins, ctx)
+                    (self._prep_trunk if self.trunk_shard is None else self._prep_trunk_sharded)(ins, ctx)
                     ctx._latent.record_stream(main)
                     ctx._img4.record_stream(main)
                     ctx.ev_trunk = torch.cuda.Event()
@@ -316,7 +383,12 @@ class RenderEngine:
             ctx.ev_lbs.record()
         if trunk:
             with torch.cuda.stream(s_trunk):
-                graphs[2].replay()
+                if self.trunk_shard is None:
+                    graphs[2].replay()
+                else:
+                    self._prep_trunk_sharded(static, ctx)
+                    ctx._latent.record_stream(main)
+                    ctx._img4.record_stream(main)
                 ctx.ev_trunk = torch.cuda.Event()
                 ctx.ev_trunk.record()
         _lib.count_launches(4)
@@ -372,6 +444,33 @@ class RenderEngine:
                                                 tab["v_template"].shape[0], _lib.ptr(ctx.frame_dev), _stream()),
                    "frame_transforms")
         cur.wait_stream(side)
+
+    def set_trunk_shard(self, rank=None, world=None):
+        """Split the encoder trunk of every following frame over `world` ranks (this rank computes 1/world of the
+        latent rows, the bands are all-gathered with torch.distributed); None switches back to the replicated trunk."""
+        self.trunk_shard = None if (rank is None or not world or world <= 1) else (int(rank), int(world))
+
+    def _prep_trunk_sharded(self, ins, ctx):
+        """The trunk branch when one frame is split over several GPUs: this rank's band of latent rows, an
+        all-gather of the bands (NVLink; the only collective on the render path, and it runs beside K1 / K3 on the
+        trunk stream), NHWC assembly.  Eager (no CUDA graph around the collective)."""
+        import torch.distributed as dist
+        from .parallel import ray_block
+        rank, world = self.trunk_shard
+        img_all = ins[0]
+        V = img_all.shape[0]
+        H, W = img_all.shape[-2:]
+        Hf, Wf = self._feat_size(H, W)
+        a, b = ray_block(Hf, rank, world)
+        mr = (Hf + world - 1) // world
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=(self.precision != "fp32")):
+            band = self._encode_rows(img_all, a, b)                                  # (V, 128, b - a, Wf)
+        mine = torch.zeros(V, mr, Wf, 128, device=img_all.device)
+        mine[:, :b - a] = band.permute(0, 2, 3, 1)
+        gathered = torch.empty(world, V, mr, Wf, 128, device=img_all.device)
+        dist.all_gather_into_tensor(gathered, mine)
+        ctx._latent = assemble_latent_rows(gathered, Hf)
+        ctx._img4 = F.pad(img_all.permute(0, 2, 3, 1), (0, 1)).contiguous().float()
 
     def _prep_trunk(self, ins, ctx):
         """What K4 needs: encoder trunk once per frame (cuDNN; boundary of the hot path), NHWC for the gather

@@ -667,3 +667,25 @@ def test_estimate_occupancy_volume():
     np.testing.assert_allclose(occ.reshape(-1)[inmask], want[inmask], rtol=1e-5, atol=1e-6)
     far = (d2 > 0.05 ** 2 * 1.02).cpu().numpy()
     assert set(np.unique(occ.reshape(-1)[far])) <= {0.0, 100.0}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,H", [("thuman", 512), ("h36m", 1000), ("thuman", 130)])
+def test_trunk_row_bands_equal_the_full_trunk(kind, H):
+    """Sharded encoder trunk (one frame over N GPUs): the bands of latent rows each rank computes -- with their 6-row halo
+    and the stride-2 phase of conv1 -- assemble to the latent of the unsplit trunk (true fp32: agreement to rounding)."""
+    from mpsnerf_b200 import synthetic
+    from mpsnerf_b200.parallel import ray_block
+    scene = synthetic.make_scene(kind, seed=0, H=H, W=H)
+    net = make_net(scene, synthetic.seeded_state_dict(0, 300.0), "fp32")
+    eng = net.engine()
+    img = scene.sp_input["img_all"][0].cuda()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        full = eng._encode(img)
+        Hf = full.shape[2]
+        for world in (2, 3, 8):
+            bands = [eng._encode_rows(img, *ray_block(Hf, r, world)) for r in range(world)]
+            got = torch.cat(bands, dim=2)
+            assert got.shape == full.shape
+            err = float((got - full).abs().max())
+            assert err <= 2e-5 * max(1.0, float(full.abs().max())), (world, err)

@@ -142,3 +142,20 @@ def test_hot_input_selection_for_host_dicts():
     for key in ("img_all", "R_all", "T_all", "K_all", "t_vertices", "params"):
         assert f'sp["{key}"]' in src and key in R.HOT_KEYS_SP
     assert 'tp["vertices"]' in src and "vertices" in R.HOT_KEYS_TP
+
+
+def test_assemble_latent_rows_matches_the_row_split():
+    """engine.assemble_latent_rows: rank-major, padded bands of latent rows (what the all-gather of the sharded encoder
+    trunk returns) -> the full (V, Hf, Wf, C) latent, for even and ragged splits."""
+    import torch
+    from mpsnerf_b200.engine import assemble_latent_rows
+    from mpsnerf_b200.parallel import ray_block
+    g = torch.Generator().manual_seed(0)
+    for Hf, world in ((250, 8), (128, 8), (7, 3), (5, 8), (16, 2)):
+        full = torch.randn(3, Hf, 4, 6, generator=g)
+        mr = (Hf + world - 1) // world
+        bands = torch.zeros(world, 3, mr, 4, 6)
+        for r in range(world):
+            a, b = ray_block(Hf, r, world)
+            bands[r, :, :b - a] = full[:, a:b]
+        assert torch.equal(assemble_latent_rows(bands, Hf), full)
