@@ -84,13 +84,22 @@ class FrameContext:
     grid: all K1 needs) on the caller's stream, the *LBS* branch (transform sets + template grid: needed from K3 on)
     and the *trunk* branch (encoder latent + NHWC images: needed from K4 on) on side streams.  ``wait_lbs`` /
     ``wait_trunk`` make the current stream wait for a branch; reading ``latent`` / ``img4`` waits for the trunk."""
-    __slots__ = ("frame_dev", "grid_tp", "grid_tv", "_latent", "_img4", "skin_w", "n_views", "keep", "ev_lbs", "ev_trunk")
+    __slots__ = ("frame_dev", "grid_tp", "grid_tv", "_latent", "_img4", "skin_w", "n_views", "keep", "ev_lbs", "ev_trunk",
+                 "pending_trunk")
+
+    def launch_pending(self):
+        """Enqueue a trunk branch whose launch was deferred (sharded trunk: ~15 eager launches + a collective, whose
+        host time would otherwise sit between the front and K1): the engine calls this right behind K1."""
+        if getattr(self, "pending_trunk", None) is not None:
+            fn, self.pending_trunk = self.pending_trunk, None
+            fn()
 
     def wait_lbs(self):
         if self.ev_lbs is not None:
             torch.cuda.current_stream().wait_event(self.ev_lbs)
 
     def wait_trunk(self):
+        self.launch_pending()
         if self.ev_trunk is not None:
             torch.cuda.current_stream().wait_event(self.ev_trunk)
 
@@ -381,16 +390,22 @@ class RenderEngine:
             graphs[1].replay()
             ctx.ev_lbs = torch.cuda.Event()
             ctx.ev_lbs.record()
-        if trunk:
+        ctx.pending_trunk = None
+        if trunk and self.trunk_shard is None:
             with torch.cuda.stream(s_trunk):
-                if self.trunk_shard is None:
-                    graphs[2].replay()
-                else:
+                graphs[2].replay()
+                ctx.ev_trunk = torch.cuda.Event()
+                ctx.ev_trunk.record()
+        elif trunk:
+            def sharded():
+                with torch.cuda.stream(s_trunk):
                     self._prep_trunk_sharded(static, ctx)
                     ctx._latent.record_stream(main)
                     ctx._img4.record_stream(main)
-                ctx.ev_trunk = torch.cuda.Event()
-                ctx.ev_trunk.record()
+                    ctx.ev_trunk = torch.cuda.Event()
+                    ctx.ev_trunk.record()
+            ctx.ev_trunk = None
+            ctx.pending_trunk = sharded          # launched by run() right behind K1 (FrameContext.launch_pending)
         _lib.count_launches(4)
         return ctx
 
@@ -406,7 +421,7 @@ class RenderEngine:
         ctx.grid_tp = torch.empty(gb, dtype=torch.uint8, device=dev)
         ctx.grid_tv = torch.empty(gb, dtype=torch.uint8, device=dev)
         ctx.keep = (list(ins), smpl)
-        ctx._latent = ctx._img4 = ctx.ev_lbs = ctx.ev_trunk = None
+        ctx._latent = ctx._img4 = ctx.ev_lbs = ctx.ev_trunk = ctx.pending_trunk = None
         return ctx
 
     @staticmethod
@@ -514,7 +529,8 @@ class RenderEngine:
         # the device) whenever nothing needs the stages one by one (per-stage timers, debug captures, direct point
         # queries); MPSNERF_FUSED_CALL=0 keeps the staged calls.
         fused = (self.precision == "bf16" and self.debug is None and self.timers is None and self._use_device_count
-                 and self._use_fused and composite and points is None and not all_active)
+                 and self._use_fused and composite and points is None and not all_active
+                 and ctx.pending_trunk is None)
         if fused:
             cap = int(min(self.slab, P))
             wsb = lib.mpsnerf_render_rays_workspace(N, S, V, cap)
@@ -559,6 +575,7 @@ class RenderEngine:
                 _lib.ptr(ctx.grid_tp), _lib.ptr(raw), _lib.ptr(mask), _lib.ptr(sq), _lib.ptr(ss), _lib.ptr(act_pid),
                 _lib.ptr(act_idx2), _lib.ptr(act_q), _lib.ptr(counter), _stream()), "sample_knn")
             _lib.count_launches(1)
+            ctx.launch_pending()
             # Device-side count (tensor-core path): K3, K4, T and M are enqueued right behind K1 for the first
             # `cap` active points and read the real count on the device; the host reads it from pinned memory
             # only after everything is in the queue, so the GPU never waits for the CPU in the middle of a
