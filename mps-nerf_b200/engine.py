@@ -278,13 +278,14 @@ class RenderEngine:
 
     # ------------------------------------------------------------------ per-frame preparation
     @torch.no_grad()
-    def prepare_frame(self, sp, tp, smpl, trunk=True):
+    def prepare_frame(self, sp, tp, smpl, trunk=True, n_points=None):
         """sp/tp: squeezed input dicts on the CUDA device; smpl: CPU tensor dict of the gender.
-        ``trunk=False`` skips the encoder branch (the training step runs the trunk under autograd itself)."""
+        ``trunk=False`` skips the encoder branch (the training step runs the trunk under autograd itself);
+        ``n_points`` = sample points the frame will push through K1 (a hint for the branch order, see below)."""
         with self.span("prep"):
-            return self._prepare_frame(sp, tp, smpl, trunk)
+            return self._prepare_frame(sp, tp, smpl, trunk, n_points)
 
-    def _prepare_frame(self, sp, tp, smpl, trunk=True):
+    def _prepare_frame(self, sp, tp, smpl, trunk=True, n_points=None):
         """~45 small launches (trunk, layout changes, K0, two grid builds) whose GPU time is ~0.45 ms but whose
         launch overhead is ~1 ms when issued one by one behind an idle GPU: they are captured once per
         (shape, device, weights) into THREE CUDA graphs over static input / output buffers -- front (frame header,
@@ -294,7 +295,11 @@ class RenderEngine:
         A FrameContext therefore stays valid until the next prepare_frame of this engine (the network keeps a
         single-entry frame cache, lib/skinnning_batch.py::frame_context).  MPSNERF_PREP_GRAPH=0 disables the graphs
         (same three branches, launched eagerly)."""
-        dev = sp["img_all"].device
+        # img_all may stay in PINNED HOST memory: it is then uploaded on the trunk stream, straight into the trunk's
+        # static input, beside the front and K1 (which do not read it) -- the 9 MB of source views are the bulk of what an
+        # end-to-end render() call has to bring over PCIe
+        dev = tp["vertices"].device
+        host_img = not sp["img_all"].is_cuda
         V = sp["img_all"].shape[0]
         vmax = _lib.MAX_VIEWS if self.precision == "fp32" else _lib.MAX_VIEWS_TC
         if not 2 <= V <= vmax:      # checked before anything is enqueued (the dense kernels would fail late and vaguely)
@@ -315,6 +320,8 @@ class RenderEngine:
         main.wait_stream(s_lbs)
         main.wait_stream(s_trunk)
         if not self._use_prep_graph:
+            if host_img:
+                ins[0] = ins[0].to(dev, non_blocking=True)
             ctx = self._new_ctx(ins, smpl)
             self._prep_front(ins, ctx)
             for st in (s_lbs, s_trunk):          # behind the front: its single-CTA grid build runs alone (3x faster)
@@ -338,7 +345,7 @@ class RenderEngine:
         g = self._prep_graphs.get(key)
         if g is None:
             try:
-                static = [torch.empty_like(t) for t in ins]
+                static = [torch.empty_like(t, device=dev) for t in ins]
                 torch._foreach_copy_(static, ins)
                 ctx = self._new_ctx(static, smpl)
                 warm = torch.cuda.Stream(device=dev)
@@ -372,13 +379,25 @@ class RenderEngine:
                               "running it eagerly from now on (MPSNERF_PREP_GRAPH=0 silences this)")
                 self._use_prep_graph = False
                 torch.cuda.synchronize(dev)
-                return self._prepare_frame(sp, tp, smpl, trunk)
+                return self._prepare_frame(sp, tp, smpl, trunk, n_points)
         graphs, static, ctx = g
-        torch._foreach_copy_(static, ins)
-        # The side branches start BEHIND the front (default): its single-CTA grid build then runs alone (3x faster than
+        if host_img:
+            torch._foreach_copy_(static[1:], ins[1:])
+        else:
+            torch._foreach_copy_(static, ins)
+        # The side branches normally start BEHIND the front: its single-CTA grid build then runs alone (3x faster than
         # beside the trunk's convolutions), and the trunk / LBS kernels fill in beside K1 as its short-lived blocks
-        # retire.  MPSNERF_PREP_ORDER=together starts all three branches at once (A/B).
-        front_first = os.environ.get("MPSNERF_PREP_ORDER", "front_first") != "together"
+        # retire.  MPSNERF_PREP_ORDER=front_first | together forces one order (A/B).
+        # When the trunk is the longer pole -- large views, or this GPU's share of the rays is small (one frame over 8
+        # GPUs: trunk 0.6 ms vs K1 + K3 0.5 ms at 3 x 1000 x 1000) -- all branches start together instead: the grid
+        # build slows down, but K4 no longer waits for the trunk (8 GPUs: 2.58 -> 2.51 ms; 1 GPU: the other way round).
+        # Estimates: trunk 0.2 us per 1000 source pixels, K1 + K3 64 ns per 1000 sample points (measured, B200).
+        order = os.environ.get("MPSNERF_PREP_ORDER", "auto")
+        if order == "auto":
+            V_, H_, W_ = ins[0].shape[0], ins[0].shape[-2], ins[0].shape[-1]
+            trunk_long = n_points is not None and 0.2e-6 * V_ * H_ * W_ > 0.5 * 0.064e-6 * n_points
+            order = "together" if (trunk and trunk_long) else "front_first"
+        front_first = order != "together"
         if not front_first:
             for st in (s_lbs, s_trunk):
                 st.wait_stream(main)
@@ -391,6 +410,9 @@ class RenderEngine:
             ctx.ev_lbs = torch.cuda.Event()
             ctx.ev_lbs.record()
         ctx.pending_trunk = None
+        if host_img and trunk:
+            with torch.cuda.stream(s_trunk):            # H2D on the copy engine, ordered in front of the trunk graph
+                static[0].copy_(ins[0], non_blocking=True)
         if trunk and self.trunk_shard is None:
             with torch.cuda.stream(s_trunk):
                 graphs[2].replay()

@@ -182,7 +182,7 @@ class SKinningBatch(nn.Module):
                 sp["poses"], sp["shapes"], sp["R"], sp["Th"], tp_input["vertices"], tp["poses"], tp["shapes"], tp["R"],
                 tp["Th"], sp_input["gender"])
 
-    def frame_context(self, sp_input, tp_input):
+    def frame_context(self, sp_input, tp_input, n_points=None):
         """Prepared per-frame state for already-squeezed dicts, cached on the identity (storage, version, shape) of
         EVERY tensor it was derived from, the engine that prepared it and the mode.  The cache holds one entry: with
         the graph-captured preparation a context is a view of static buffers that the next prepare_frame of the same
@@ -193,9 +193,10 @@ class SKinningBatch(nn.Module):
             (self.training, id(eng), eng.precision)
         if key != self._frame_key:
             self._check_supported()
-            if not sp_input["img_all"].is_cuda:
-                raise RuntimeError("mpsnerf_b200 has no CPU path: inputs must be CUDA tensors")
-            self._frame_ctx = eng.prepare_frame(sp_input, tp_input, self._smpl_for(sp_input["gender"]))
+            if not tp_input["vertices"].is_cuda or not (sp_input["img_all"].is_cuda or sp_input["img_all"].is_pinned()):
+                raise RuntimeError("mpsnerf_b200 has no CPU path: inputs must be CUDA tensors "
+                                   "(img_all may also be a pinned host tensor: it is uploaded beside K1)")
+            self._frame_ctx = eng.prepare_frame(sp_input, tp_input, self._smpl_for(sp_input["gender"]), n_points=n_points)
             self._frame_key = key
             self._frame_keep = probe
         return self._frame_ctx

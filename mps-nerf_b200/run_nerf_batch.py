@@ -134,7 +134,7 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, pert
     per = []
     for b in range(B):
         sp, tp = _select(sp_input, b), _select(tp_input, b)
-        ctx = net.frame_context(sp, tp)
+        ctx = net.frame_context(sp, tp, n_points=C * S)
         if _rays_ready is not None:       # rays uploaded on the copy stream while the frame was being prepared
             torch.cuda.current_stream(dev).wait_event(_rays_ready)
             _rays_ready = None
@@ -175,8 +175,10 @@ def _upload_hot(d, keys, dev):
         if isinstance(v, dict):
             return {k: mv(x) for k, x in v.items()}
         return v
-    # gender stays on the host: it only selects which SMPL tables to use, a host-side decision
-    return {k: (d[k] if k == "gender" else mv(d[k])) for k in keys if k in d}
+    # gender stays on the host: it only selects which SMPL tables to use, a host-side decision; so do pinned source
+    # views: the engine uploads them on its trunk stream, beside the front and K1 (engine._prepare_frame)
+    keep = lambda k, v: k == "gender" or (k == "img_all" and torch.is_tensor(v) and v.is_pinned())
+    return {k: (d[k] if keep(k, d[k]) else mv(d[k])) for k in keys if k in d}
 
 
 def hot_input_bytes(sp_input, tp_input):
@@ -227,7 +229,7 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
                           torch.reshape(near, [B, -1, 1]).float(), torch.reshape(far, [B, -1, 1]).float()], -1)
 
     ready = None
-    if not sp_input["img_all"].is_cuda:
+    if not sp_input["K_all"].is_cuda:
         # host dicts (ideally pinned): upload only what the path reads, on the current stream (the frame
         # preparation needs them first); the rays follow on the copy stream below
         if not torch.cuda.is_available():
@@ -240,14 +242,14 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
             raise ValueError("render() needs either rays / near / far or camera=dict(K, R, T, bounds, H, W)")
         from .lib.if_nerf_data_utils import gen_rays8
         rays8, box = gen_rays8(camera["H"], camera["W"], camera["K"], camera["R"], camera["T"], camera["bounds"],
-                               device=sp_input["img_all"].device, rows=camera.get("rows"))
+                               device=sp_input["K_all"].device, rows=camera.get("rows"))
         packed = rays8[None]
         sh = (1, packed.shape[1], 3)
-    elif not rays.is_cuda and sp_input["img_all"].is_cuda:
+    elif not rays.is_cuda and sp_input["K_all"].is_cuda:
         # Host (ideally pinned) rays / near / far: uploaded and packed on a copy stream, so that the transfer
         # overlaps the per-frame preparation (trunk, K0, grids), which needs only sp_input / tp_input.
         sh = rays[:, 1, ...].shape
-        dev = sp_input["img_all"].device
+        dev = sp_input["K_all"].device
         main = torch.cuda.current_stream(dev)
         cs = _copy_stream(dev)
         cs.wait_stream(main)

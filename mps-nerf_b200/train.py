@@ -160,7 +160,7 @@ class TrainEngine:
         net = self.net
         net._check_supported()
         fctx = self.eng.prepare_frame(sp, tp, net._smpl_for(sp["gender"]), trunk=False)
-        img = sp["img_all"].float()
+        img = sp["img_all"].to(tp["vertices"].device, non_blocking=True).float()
         latent = net.encoder_2d(img)                               # torch / cuDNN under autograd: the path's boundary
         latent = latent.permute(0, 2, 3, 1).contiguous().float()
         img4 = F.pad(img.permute(0, 2, 3, 1), (0, 1)).contiguous()
