@@ -201,8 +201,10 @@ def _copy_stream(dev):
 def batchify_rays(rays_flat, chunk=1024 * 32, sp_input=None, tp_input=None, **kwargs):
     """ref :85-97: render in chunks of ``chunk`` rays and concatenate along the ray dim."""
     all_ret = {}
+    pu = kwargs.pop("perturb_u", None)          # supplied stratified-sampling uniforms follow their rays
     for i in range(0, rays_flat.shape[1], chunk):
-        ret = render_rays(rays_flat[:, i:i + chunk], sp_input=sp_input, tp_input=tp_input, **kwargs)
+        ret = render_rays(rays_flat[:, i:i + chunk], sp_input=sp_input, tp_input=tp_input,
+                          perturb_u=None if pu is None else pu[:, i:i + chunk], **kwargs)
         for k, v in ret.items():
             all_ret.setdefault(k, []).append(v)
     return {k: torch.cat(v, 1) for k, v in all_ret.items()}
@@ -262,7 +264,20 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
         sh = rays[:, 1, ...].shape
         packed = pack(rays, near, far)
     n = packed.shape[1]
-    ret = render_rays(packed, sp_input=sp_input, tp_input=tp_input, _rays_ready=ready, **kwargs)
+    S_ = int(kwargs.get("N_samples", 64))
+    per_ray = S_ * (44 + 20 + 8)              # extras + active list + slack, bytes per ray
+    free = torch.cuda.mem_get_info(packed.device)[0] if packed.is_cuda else 1 << 62
+    if n * S_ >= (1 << 31) or n * per_ray > 0.6 * free:
+        # The kernels take the whole ray set at once (they chunk internally by ACTIVE points); only a set whose
+        # per-sample outputs cannot be held -- 2^31 sample points, or more than the free device memory -- is cut into
+        # ray chunks here (the reference's `chunk` semantics), the results concatenated as batchify_rays does.
+        fit = max(1024, int(0.25 * free // per_ray))
+        fit = min(fit, ((1 << 31) - 1) // S_)
+        if ready is not None:
+            torch.cuda.current_stream(packed.device).wait_event(ready)
+        ret = batchify_rays(packed, fit, sp_input=sp_input, tp_input=tp_input, **kwargs)
+    else:
+        ret = render_rays(packed, sp_input=sp_input, tp_input=tp_input, _rays_ready=ready, **kwargs)
     nchunks = max(1, (n + chunk - 1) // chunk)
     ret["other_loss"] = torch.zeros(1, 4 * nchunks, device=packed.device)
     for k in ("rgb_map", "disp_map", "acc_map", "pts_mask", "raw"):

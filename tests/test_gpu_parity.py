@@ -689,3 +689,22 @@ def test_trunk_row_bands_equal_the_full_trunk(kind, H):
             assert got.shape == full.shape
             err = float((got - full).abs().max())
             assert err <= 2e-5 * max(1.0, float(full.abs().max())), (world, err)
+
+
+@pytest.mark.gpu
+def test_batchify_rays_chunks_equal_one_pass():
+    """batchify_rays (ref :85-97; also render()'s fallback for ray sets whose per-sample outputs would not fit): chunked
+    rendering with supplied stratified-sampling uniforms equals the single pass bit for bit."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    scene, sd, g = load_case("stress")
+    net = R.NetworkHandle(make_net(scene, sd, "bf16"))
+    ids, S = g["ray_ids"], int(g["S"])
+    rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
+    u = torch.from_numpy(g["u"])[None].cuda()
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+    kw = dict(network_fn=net, N_samples=S, perturb=1.0, sp_input=sp, tp_input=tp)
+    one = R.render(rays=rays, near=near, far=far, use_viewdirs=True, perturb_u=u, **kw)
+    packed = torch.cat([rays[:, 0], rays[:, 1], near, far], -1)
+    parts = R.batchify_rays(packed, 100, perturb_u=u, **kw)
+    assert torch.equal(parts["raw"], one[3]["raw"].reshape(parts["raw"].shape))
+    assert torch.equal(parts["rgb_map"], one[0]) and torch.equal(parts["pts_mask"], one[3]["pts_mask"].reshape(parts["pts_mask"].shape))
