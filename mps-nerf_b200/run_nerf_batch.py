@@ -266,7 +266,9 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
     n = packed.shape[1]
     S_ = int(kwargs.get("N_samples", 64))
     per_ray = S_ * (44 + 20 + 8)              # extras + active list + slack, bytes per ray
-    free = torch.cuda.mem_get_info(packed.device)[0] if packed.is_cuda else 1 << 62
+    # (cudaMemGetInfo costs ~0.4 ms per call: asked only for ray sets that could plausibly not fit)
+    big = n * per_ray > (8 << 30)
+    free = torch.cuda.mem_get_info(packed.device)[0] if (big and packed.is_cuda) else 1 << 62
     if n * S_ >= (1 << 31) or n * per_ray > 0.6 * free:
         # The kernels take the whole ray set at once (they chunk internally by ACTIVE points); only a set whose
         # per-sample outputs cannot be held -- 2^31 sample points, or more than the free device memory -- is cut into
