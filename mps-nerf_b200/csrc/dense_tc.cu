@@ -215,8 +215,8 @@ struct TArgs {
 
 // LayerNorm over the 155 real columns of a row whose 160 columns are split between four threads
 // (this thread: x[0..40) = columns 40 q ..; real columns: 40 or 35), result bf16-packed -> YT.
-// gamma/beta are zero in the 5 pad columns, so the pad of the operand is exactly zero.  Centred (two-pass accurate)
-// statistics like the reference's nn.LayerNorm; the partial results of a row meet in LS once.
+// gamma/beta are zero in the 5 pad columns, so the pad of the operand is exactly zero.  Two passes
+// (mean, then centred variance) like the reference's nn.LayerNorm; the partial sums of a row meet in LS.
 __device__ __forceinline__ void ln_to_tmem(float (&x)[40], const float* __restrict__ pend,
                                            const float* __restrict__ g, const float* __restrict__ b, float* LS,
                                            int r, int q, int warp, uint32_t tl) {
@@ -229,28 +229,18 @@ __device__ __forceinline__ void ln_to_tmem(float (&x)[40], const float* __restri
       x[4 * c] += t.x; x[4 * c + 1] += t.y; x[4 * c + 2] += t.z; x[4 * c + 3] += t.w;
     }
   }
-  // Row statistics with ONE exchange between the four threads of a row: every thread forms the sum and the centred
-  // sum of squares (about its OWN mean) of its 40 / 35 columns, both meet in LS behind one barrier, and the exact
-  // pooled variance follows from Chan's update  M2 = sum_k [ M2_k + n_k (mean_k - mean)^2 ]  -- the same two-pass
-  // accuracy as nn.LayerNorm, one named barrier and one shared-memory round trip less than mean-then-variance.
   float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < 40; ++c) if (c < nreal) s[c & 3] += x[c];
-  const float sq = (s[0] + s[1]) + (s[2] + s[3]);
-  const float mq = sq * ((q == 3) ? (1.0f / 35.0f) : (1.0f / 40.0f));
+  LS[q * 128 + r] = (s[0] + s[1]) + (s[2] + s[3]);
+  f_row_bar(warp);
+  const float mean = ((LS[r] + LS[128 + r]) + (LS[256 + r] + LS[384 + r])) * (1.0f / 155.0f);
   float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 40; ++c) if (c < nreal) { const float d = x[c] - mq; v[c & 3] = fmaf(d, d, v[c & 3]); }
-  LS[q * 128 + r] = sq;
+  for (int c = 0; c < 40; ++c) if (c < nreal) { const float d = x[c] - mean; v[c & 3] = fmaf(d, d, v[c & 3]); }
   LS[512 + q * 128 + r] = (v[0] + v[1]) + (v[2] + v[3]);
   f_row_bar(warp);
-  const float s0 = LS[r], s1 = LS[128 + r], s2 = LS[256 + r], s3 = LS[384 + r];
-  const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 155.0f);
-  const float d0 = s0 * (1.0f / 40.0f) - mean, d1 = s1 * (1.0f / 40.0f) - mean, d2 = s2 * (1.0f / 40.0f) - mean,
-              d3 = s3 * (1.0f / 35.0f) - mean;
-  const float m2 = ((LS[512 + r] + LS[640 + r]) + (LS[768 + r] + LS[896 + r])) +
-                   (40.0f * ((d0 * d0 + d1 * d1) + d2 * d2) + 35.0f * (d3 * d3));
-  const float rstd = rsqrtf(m2 * (1.0f / 155.0f) + 1e-5f);
+  const float rstd = rsqrtf(((LS[512 + r] + LS[640 + r]) + (LS[768 + r] + LS[896 + r])) * (1.0f / 155.0f) + 1e-5f);
   const float4* g4 = reinterpret_cast<const float4*>(g + 40 * q);
   const float4* b4 = reinterpret_cast<const float4*>(b + 40 * q);
   uint32_t pk[20];
