@@ -708,3 +708,35 @@ def test_batchify_rays_chunks_equal_one_pass():
     parts = R.batchify_rays(packed, 100, perturb_u=u, **kw)
     assert torch.equal(parts["raw"], one[3]["raw"].reshape(parts["raw"].shape))
     assert torch.equal(parts["rgb_map"], one[0]) and torch.equal(parts["pts_mask"], one[3]["pts_mask"].reshape(parts["pts_mask"].shape))
+
+
+@pytest.mark.gpu
+def test_fused_render_rays_call_equals_staged_calls(monkeypatch):
+    """mpsnerf_render_rays_bf16 (one C call per frame: K1, K3, K4, T, M, K6 with the active count on the device) against
+    the same stages called one by one -- bit-identical outputs, incl. stratified jitter and the overflow beyond a small
+    slab capacity."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    scene, sd, g = load_case("stress")
+    ids, S = g["ray_ids"], int(g["S"])
+    rays, near, far = synthetic.rays_tensor(scene, ids, device="cuda")
+    u = torch.from_numpy(g["u"])[None].cuda()
+    sp, tp = _cuda_dict(scene.sp_input), _cuda_dict(scene.tp_input)
+
+    def run(fused, slab=None):
+        monkeypatch.setenv("MPSNERF_FUSED_CALL", "1" if fused else "0")
+        net = R.NetworkHandle(make_net(scene, sd, "bf16"))
+        eng = net.module.engine()
+        assert eng._use_fused == fused
+        if slab:
+            eng.slab = slab
+        out = R.render(rays=rays, near=near, far=far, sp_input=sp, tp_input=tp, network_fn=net, N_samples=S, perturb=1.0,
+                       perturb_u=u, use_viewdirs=True)
+        torch.cuda.synchronize()
+        return out, eng.last_active
+
+    (a, na), (b, nb), (c, nc) = run(True), run(False), run(True, slab=300)
+    assert na == nb == nc and na > 600                    # the small capacity overflows: remainder slabs + K6 again
+    for x, y, z in ((a[0], b[0], c[0]), (a[2], b[2], c[2]), (a[3]["raw"], b[3]["raw"], c[3]["raw"]),
+                    (a[3]["smpl_src_pts"], b[3]["smpl_src_pts"], c[3]["smpl_src_pts"]), (a[3]["pts_mask"], b[3]["pts_mask"], c[3]["pts_mask"])):
+        assert torch.equal(x, y) and torch.equal(x, z)
+    assert torch.equal(a[1].nan_to_num(-1.0), b[1].nan_to_num(-1.0))
