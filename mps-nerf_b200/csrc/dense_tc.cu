@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         P.push(src, kWoChunk);
         for (int c = 0; c < 3; ++c) P.push(src, kQkvChunk);
         for (int c = 0; c < 3; ++c) P.push(src, kWoChunk);
-        for (int c = 0; c < 6; ++c) P.push(src, kW1Chunk / 2);          // W1 rows 0..63 (3 chunks), then rows 64..127
+        for (int c = 0; c < 2; ++c) P.push(src, 3 * (kW1Chunk / 2));    // W1 rows 0..63 (3 K-chunks = one slot), then rows 64..127
         for (int c = 0; c < 2; ++c) P.push(src, kW2Chunk);
       }
     }
@@ -353,6 +353,25 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         Cn.advance();
       }
     };
+    // Same, with all K-chunks of the operand in ONE ring slot (chunk stride kN * 128 bytes): the two 64-row halves of
+    // W1 are 3 x 8 KB each -- as three slots apiece they filled the 5-slot ring with a quarter of its bytes and the
+    // feed-forward burst (W1 + W2 = 8 slots) made the tensor pipe wait for weights (3 K cycles per tile).
+    auto gemm_one_slot = [&](auto ksteps_c, auto n_c, uint32_t dcol, uint32_t acol) {
+      constexpr int kSteps = decltype(ksteps_c)::value, kN = decltype(n_c)::value;
+      constexpr uint32_t idesc = instr_desc_bf16(kN);
+      static_assert(((kSteps + 3) / 4) * kN * 128 <= (int)kT_SlotBytes, "operand must fit one slot");
+      const uint32_t base = Cn.acquire();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kSteps; ++k) {
+          const uint64_t bdesc = smem_desc_sw128(base + (uint32_t)(k >> 2) * (uint32_t)(kN * 128));
+          mma_bf16_ts(tm + dcol, tm + acol + k * 8, bdesc + (uint64_t)((k & 3) * 2), idesc, k > 0 ? 1u : 0u);
+        }
+        Cn.release_elected();
+      }
+      __syncwarp();
+      Cn.advance();
+    };
     using K10 = std::integral_constant<int, 10>; using K4 = std::integral_constant<int, 4>; using K8 = std::integral_constant<int, 8>;
     using N192 = std::integral_constant<int, 192>; using N160 = std::integral_constant<int, 160>; using N128 = std::integral_constant<int, 128>; using N64 = std::integral_constant<int, 64>;
     for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
@@ -379,10 +398,10 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         // epilogue threads that own them (q < 2) while [64,128) is still being computed, and x += gelu(.) W2^T runs
         // over the first half's K = 64 while the other threads are still in their GELU.
         wait_a();
-        gemm(K10{}, N64{}, kT_ColR, kT_ColY, false);
+        gemm_one_slot(K10{}, N64{}, kT_ColR, kT_ColY);
         if (elect_one()) mma_commit(&pipe->h_bar[0]);
         __syncwarp();
-        gemm(K10{}, N64{}, kT_ColR + 64, kT_ColY, false);
+        gemm_one_slot(K10{}, N64{}, kT_ColR + 64, kT_ColY);
         if (elect_one()) mma_commit(&pipe->h_bar[1]);
         __syncwarp();
         pf.start(); mbar_wait(&pipe->g_bar[0], pg & 1); pf.stop(acc_a); tc_fence_after();
