@@ -215,8 +215,9 @@ struct TArgs {
 
 // LayerNorm over the 155 real columns of a row whose 160 columns are split between four threads
 // (this thread: x[0..40) = columns 40 q ..; real columns: 40 or 35), result bf16-packed -> YT.
-// gamma/beta are zero in the 5 pad columns, so the pad of the operand is exactly zero.  Two passes
-// (mean, then centred variance) like the reference's nn.LayerNorm; the partial sums of a row meet in LS.
+// The affine part (gamma, beta) lives in the weights of the consuming GEMM (pack.py); the pad of the operand is exactly
+// zero, except the constant 1.0 of column 155.  Two passes (mean, then centred variance) like the reference's
+// nn.LayerNorm; the partial sums of a row meet in LS.
 __device__ __forceinline__ void ln_to_tmem(float (&x)[40], const float* __restrict__ pend,
                                            const float* __restrict__ g, const float* __restrict__ b, float* LS,
                                            int r, int q, int warp, uint32_t tl) {
@@ -241,16 +242,21 @@ __device__ __forceinline__ void ln_to_tmem(float (&x)[40], const float* __restri
   LS[512 + q * 128 + r] = (v[0] + v[1]) + (v[2] + v[3]);
   f_row_bar(warp);
   const float rstd = rsqrtf(((LS[512 + r] + LS[640 + r]) + (LS[768 + r] + LS[896 + r])) * (1.0f / 155.0f) + 1e-5f);
-  const float4* g4 = reinterpret_cast<const float4*>(g + 40 * q);
-  const float4* b4 = reinterpret_cast<const float4*>(b + 40 * q);
+  // gamma / beta are folded into the consuming GEMM's weights (pack.py): the operand is xhat = (x - mean) rstd, exactly
+  // zero in the pad columns except a constant 1.0 in column 155 (K row that carries W beta for the q|k|v projection).
+  (void)g; (void)b;
+  const float nm = -mean * rstd;
   uint32_t pk[20];
 #pragma unroll
   for (int c = 0; c < 10; ++c) {
-    const float4 gg = g4[c], bb = b4[c];
-    const float y0 = fmaf((x[4 * c] - mean) * rstd, gg.x, bb.x), y1 = fmaf((x[4 * c + 1] - mean) * rstd, gg.y, bb.y);
-    const float y2 = fmaf((x[4 * c + 2] - mean) * rstd, gg.z, bb.z), y3 = fmaf((x[4 * c + 3] - mean) * rstd, gg.w, bb.w);
-    pk[2 * c] = pack_bf16x2(y0, y1);
-    pk[2 * c + 1] = pack_bf16x2(y2, y3);
+    float y[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = 4 * c + e;
+      y[e] = (col < nreal) ? fmaf(x[col], rstd, nm) : ((q == 3 && col == 35) ? 1.0f : 0.0f);
+    }
+    pk[2 * c] = pack_bf16x2(y[0], y[1]);
+    pk[2 * c + 1] = pack_bf16x2(y[2], y[3]);
   }
 #pragma unroll
   for (int i = 0; i < 5; ++i) tmem_st_x4(tl + kT_ColY + 20 * q + 4 * i, &pk[4 * i]);   // every TMEM access aligned to its own width

@@ -7,6 +7,8 @@ Layout (bytes; every weight tile is K-major bf16 in SWIZZLE_128B chunks, see
       qkv_0, qkv_1, qkv_2 [3 chunks x 192 rows each]; Wo_0 [1 x 160]; qkv_3; Wo_1; Wo_2; Wo_3;
       W1 rows 0..63 [3 x 64], W1 rows 64..127 [3 x 64]; W2[2 x 160]
       qkv_h rows = (q_h | k_h | v_h) = to_qkv rows 64h.., 256+64h.., 512+64h..   (K = 155 -> 192)
+      LayerNorm affine folded in: columns scaled by gamma, K column 155 = W beta (against a constant 1.0 the
+      LayerNorm epilogue writes there); W1 scaled by gamma, W1 beta added to b1
   MLP (1 441 792 B = 44 ring slots of 2 chunks of 128 rows x 128 B), every 256-output layer split
       into its two N-halves (output rows 0..127, then 128..255), each half 4 chunks (K = 256) per K part:
       L0[h0 | h1] (K order: tok0 155, 5 zero, PE 39, zero to 256); L1..L4[h0 | h1] each;
@@ -50,6 +52,16 @@ def pack_weights_bf16(net, device=None):
         p = f"transformer.layers.{l}."
         wqkv, wo = sd[p + "0.fn.fn.to_qkv.weight"], sd[p + "0.fn.fn.to_out.0.weight"]
         w1, w2 = sd[p + "1.fn.fn.net.0.weight"], sd[p + "1.fn.fn.net.3.weight"]
+        # The LayerNorm affine is folded into the GEMM that consumes it: LN(x) W^T = xhat (W diag(g))^T + W b.  The
+        # kernel's LayerNorm epilogue then writes only xhat = (x - mean) rstd (no gamma / beta loads and FMAs: a fifth
+        # of its instructions) plus a constant 1.0 in the first pad column (K index 155), against which the q|k|v
+        # weights carry W b as an extra K column (the projection has no bias of its own to absorb it); for the
+        # feed-forward W b joins the existing fp32 bias.
+        g1, be1 = sd[p + "0.fn.norm.weight"], sd[p + "0.fn.norm.bias"]
+        g2, be2 = sd[p + "1.fn.norm.weight"], sd[p + "1.fn.norm.bias"]
+        wqkv = torch.cat([wqkv * g1[None, :], (wqkv @ be1)[:, None]], 1)          # (768, 156)
+        b1_eff = sd[p + "1.fn.fn.net.0.bias"] + w1 @ be2
+        w1 = w1 * g2[None, :]
         qkv = [torch.cat([wqkv[64 * h:64 * h + 64], wqkv[256 + 64 * h:256 + 64 * h + 64],
                           wqkv[512 + 64 * h:512 + 64 * h + 64]], 0) for h in range(4)]
         out = [wo[:, 64 * h:64 * h + 64] for h in range(4)]
@@ -66,7 +78,7 @@ def pack_weights_bf16(net, device=None):
         pend = pend_mid + _pad160(sd[p + "1.fn.fn.net.3.bias"])
         floats += [_pad160(sd[p + "0.fn.norm.weight"]), _pad160(sd[p + "0.fn.norm.bias"]), pend_in,
                    _pad160(sd[p + "1.fn.norm.weight"]), _pad160(sd[p + "1.fn.norm.bias"]), pend_mid,
-                   sd[p + "1.fn.fn.net.0.bias"]]
+                   b1_eff]          # (the ln_* vectors stay in the blob for reference; the kernels no longer read them)
     floats.append(pend)
     assert sum(x.numel() for x in parts) == T_BYTES
 
