@@ -320,22 +320,31 @@ class _Lin:
         return F.linear(x, w, b)
 
 
+def _ln_linear(x, g, b, w, bias, lin):
+    """linear(LayerNorm(x)).  fp32: literally that.  bf16 emulation: the tensor-core path folds the LayerNorm affine into
+    the weights (mps-nerf_b200/pack.py): operand = bf16(xhat), weights = bf16(W diag(g)), the W b term is a bf16 K column
+    for the bias-free q|k|v projection and part of the fp32 bias otherwise."""
+    if not lin.bf16:
+        return F.linear(F.layer_norm(x, (x.shape[-1],), g, b, 1e-5), w, bias)
+    xh = F.layer_norm(x, (x.shape[-1],), None, None, 1e-5).bfloat16().float()
+    wb = w @ b
+    extra = wb.bfloat16().float() if bias is None else (bias + wb)
+    return F.linear(xh, (w * g[None, :]).bfloat16().float(), None) + extra
+
+
 def transformer(tok, sd, lin):
     """ref lib/transformer.py:13-86: tok (P,V,155) -> (P,V,155); depth 2, 4 heads x 64."""
     x = tok
     for l in range(2):
         p = f"transformer.layers.{l}."
-        y = F.layer_norm(x, (155,), sd[p + "0.fn.norm.weight"], sd[p + "0.fn.norm.bias"], 1e-5)
-        qkv = lin(y, sd[p + "0.fn.fn.to_qkv.weight"])
+        qkv = _ln_linear(x, sd[p + "0.fn.norm.weight"], sd[p + "0.fn.norm.bias"], sd[p + "0.fn.fn.to_qkv.weight"], None, lin)
         P, V, _ = qkv.shape
         q, k, v = (t.reshape(P, V, 4, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
-        if lin.bf16:
-            pass  # attention itself stays fp32 in the kernels
-        att = torch.softmax(torch.einsum("bhid,bhjd->bhij", q, k) * (64 ** -0.5), dim=-1)
+        att = torch.softmax(torch.einsum("bhid,bhjd->bhij", q, k) * (64 ** -0.5), dim=-1)      # (attention itself stays fp32)
         o = torch.einsum("bhij,bhjd->bhid", att, v).permute(0, 2, 1, 3).reshape(P, V, 256)
         x = x + lin(o, sd[p + "0.fn.fn.to_out.0.weight"], sd[p + "0.fn.fn.to_out.0.bias"])
-        y = F.layer_norm(x, (155,), sd[p + "1.fn.norm.weight"], sd[p + "1.fn.norm.bias"], 1e-5)
-        h = F.gelu(lin(y, sd[p + "1.fn.fn.net.0.weight"], sd[p + "1.fn.fn.net.0.bias"]))
+        h = F.gelu(_ln_linear(x, sd[p + "1.fn.norm.weight"], sd[p + "1.fn.norm.bias"], sd[p + "1.fn.fn.net.0.weight"],
+                              sd[p + "1.fn.fn.net.0.bias"], lin))
         x = x + lin(h, sd[p + "1.fn.fn.net.3.weight"], sd[p + "1.fn.fn.net.3.bias"])
     return x
 
