@@ -563,26 +563,31 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
             pf.stop(sec[0]);
             named_bar_sync(6 + team, kFEpiThreads / 2);      // a point's rows may sit in different lane quarters: team-wide
             pf.stop(sec[1]);
-            // partial dots with the partner keys over this thread's 32 of the 64 head dims (fp32 accumulation)
+            // partial dots with the partner keys over this thread's 32 of the 64 head dims.  The partner keys arrive as
+            // fp16 anyway; q is rounded to fp16 as well and the products run as packed half2 FMAs into eight short
+            // partial sums (four products each, so the fp16 accumulation error stays ~2^-11 of a term), which are
+            // added up in fp32 -- a third of the instructions of unpacking every key to fp32 first.
+            {
+              __half2 qh[16];
 #pragma unroll
-            for (int j = 1; j < V; ++j) {
-              const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
-              const uint8_t* src = KXt + rj * 128;
-              uint4 kp[4];
+              for (int i = 0; i < 16; ++i) qh[i] = __floats2half2_rn(qv[2 * i], qv[2 * i + 1]);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) kp[u] = *reinterpret_cast<const uint4*>(src + (((4 * hf + u) ^ (rj & 7)) << 4));
-              float d[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int j = 1; j < V; ++j) {
+                const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
+                const uint8_t* src = KXt + rj * 128;
+                uint4 kp[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&kp[u]);
+                for (int u = 0; u < 4; ++u) kp[u] = *reinterpret_cast<const uint4*>(src + (((4 * hf + u) ^ (rj & 7)) << 4));
+                __half2 ac[4] = {__float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f)};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = __half22float2(h2[i]);
-                  d[(2 * i) & 3] = fmaf(qv[8 * u + 2 * i], f.x, d[(2 * i) & 3]);
-                  d[(2 * i + 1) & 3] = fmaf(qv[8 * u + 2 * i + 1], f.y, d[(2 * i + 1) & 3]);
+                for (int u = 0; u < 4; ++u) {
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&kp[u]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) ac[i] = __hfma2(qh[4 * u + i], h2[i], ac[i]);
                 }
+                const float2 f0 = __half22float2(ac[0]), f1 = __half22float2(ac[1]), f2 = __half22float2(ac[2]), f3 = __half22float2(ac[3]);
+                PDt[(hf * 128 + r) * 4 + j] = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
               }
-              PDt[(hf * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
             }
             pf.stop(sec[2]);
             named_bar_sync(8 + 4 * team + (warp & 3), 64);    // the two threads of a row (warps w, w + 4 of the team)
@@ -652,13 +657,11 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
           float t[32];
           tmem_ld_x32(tl + kT_ColR + 32 * q, t);
           tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(fp + 960 + 32 * q);
-          uint32_t pk[16];
+          uint32_t pk[16];         // (the bias b1 rides in the GEMM: K column 155 of W1 against the operand's constant 1.0, pack.py)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = b4[i];
-            pk[2 * i] = gelu_pair_bf16(t[4 * i] + bb.x, t[4 * i + 1] + bb.y);
-            pk[2 * i + 1] = gelu_pair_bf16(t[4 * i + 2] + bb.z, t[4 * i + 3] + bb.w);
+            pk[2 * i] = gelu_pair_bf16(t[4 * i], t[4 * i + 1]);
+            pk[2 * i + 1] = gelu_pair_bf16(t[4 * i + 2], t[4 * i + 3]);
           }
           tmem_st_u16(tl + kT_ColO + 16 * q, pk);
           tmem_st_wait();

@@ -55,13 +55,13 @@ def pack_weights_bf16(net, device=None):
         # The LayerNorm affine is folded into the GEMM that consumes it: LN(x) W^T = xhat (W diag(g))^T + W b.  The
         # kernel's LayerNorm epilogue then writes only xhat = (x - mean) rstd (no gamma / beta loads and FMAs: a fifth
         # of its instructions) plus a constant 1.0 in the first pad column (K index 155), against which the q|k|v
-        # weights carry W b as an extra K column (the projection has no bias of its own to absorb it); for the
-        # feed-forward W b joins the existing fp32 bias.
+        # weights carry W b as an extra K column; for the feed-forward the same column carries W b + b1, so the GELU
+        # epilogue adds no bias either.
         g1, be1 = sd[p + "0.fn.norm.weight"], sd[p + "0.fn.norm.bias"]
         g2, be2 = sd[p + "1.fn.norm.weight"], sd[p + "1.fn.norm.bias"]
         wqkv = torch.cat([wqkv * g1[None, :], (wqkv @ be1)[:, None]], 1)          # (768, 156)
         b1_eff = sd[p + "1.fn.fn.net.0.bias"] + w1 @ be2
-        w1 = w1 * g2[None, :]
+        w1 = torch.cat([w1 * g2[None, :], b1_eff[:, None]], 1)                      # (128, 156): the bias as K column 155
         qkv = [torch.cat([wqkv[64 * h:64 * h + 64], wqkv[256 + 64 * h:256 + 64 * h + 64],
                           wqkv[512 + 64 * h:512 + 64 * h + 64]], 0) for h in range(4)]
         out = [wo[:, 64 * h:64 * h + 64] for h in range(4)]

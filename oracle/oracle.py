@@ -322,13 +322,13 @@ class _Lin:
 
 def _ln_linear(x, g, b, w, bias, lin):
     """linear(LayerNorm(x)).  fp32: literally that.  bf16 emulation: the tensor-core path folds the LayerNorm affine into
-    the weights (mps-nerf_b200/pack.py): operand = bf16(xhat), weights = bf16(W diag(g)), the W b term is a bf16 K column
-    for the bias-free q|k|v projection and part of the fp32 bias otherwise."""
+    the weights (mps-nerf_b200/pack.py): operand = bf16(xhat), weights = bf16(W diag(g)), and W b (+ the layer's own
+    bias) is a bf16 K column against a constant 1.0 of the operand."""
     if not lin.bf16:
         return F.linear(F.layer_norm(x, (x.shape[-1],), g, b, 1e-5), w, bias)
     xh = F.layer_norm(x, (x.shape[-1],), None, None, 1e-5).bfloat16().float()
     wb = w @ b
-    extra = wb.bfloat16().float() if bias is None else (bias + wb)
+    extra = (wb if bias is None else (bias + wb)).bfloat16().float()       # a bf16 K column against a constant 1.0
     return F.linear(xh, (w * g[None, :]).bfloat16().float(), None) + extra
 
 
