@@ -211,6 +211,7 @@ struct TArgs {
   int prof;
   const int32_t* count_dev;   // optional device-side active count (count is then the slab capacity)
   int64_t first;
+  int opt;                    // experiment switches (MPSNERF_T_OPT): bit 0 = partner dots as packed half2 FMAs instead of fp32
 };
 
 // LayerNorm over the 155 real columns of a row whose 160 columns are split between four threads
@@ -567,7 +568,28 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
             // fp16 anyway; q is rounded to fp16 as well and the products run as packed half2 FMAs into eight short
             // partial sums (four products each, so the fp16 accumulation error stays ~2^-11 of a term), which are
             // added up in fp32 -- a third of the instructions of unpacking every key to fp32 first.
-            {
+            if (!(a.opt & 1)) {
+#pragma unroll
+              for (int j = 1; j < V; ++j) {
+                const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);
+                const uint8_t* src = KXt + rj * 128;
+                uint4 kp[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) kp[u] = *reinterpret_cast<const uint4*>(src + (((4 * hf + u) ^ (rj & 7)) << 4));
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&kp[u]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+                    d[(2 * i) & 3] = fmaf(qv[8 * u + 2 * i], f.x, d[(2 * i) & 3]);
+                    d[(2 * i + 1) & 3] = fmaf(qv[8 * u + 2 * i + 1], f.y, d[(2 * i + 1) & 3]);
+                  }
+                }
+                PDt[(hf * 128 + r) * 4 + j] = (d[0] + d[1]) + (d[2] + d[3]);
+              }
+            } else {
               __half2 qh[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) qh[i] = __floats2half2_rn(qv[2 * i], qv[2 * i + 1]);
@@ -1342,7 +1364,9 @@ static int dense_bf16_impl(const void* tokens, int32_t ld, const float* xc, int6
   }
   static int prof = -1;
   if (prof < 0) { const char* e = getenv("MPSNERF_TC_PROF"); prof = e ? atoi(e) : 0; }
-  TArgs ta{static_cast<const __half*>(tokens), ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof, count_dev, first};
+  static int topt = -1;
+  if (topt < 0) { const char* e = getenv("MPSNERF_T_OPT"); topt = e ? atoi(e) : 0; }
+  TArgs ta{static_cast<const __half*>(tokens), ld, count, n_views, static_cast<const uint8_t*>(packed), tok0, tok1, prof, count_dev, first, topt};
   MArgs ma{tok0, tok1, xc, count, static_cast<const uint8_t*>(packed), act_pid + first, raw, prof, count_dev, first};
   const int ppt = 128 / n_views;
   const int64_t t_tiles = (count + ppt - 1) / ppt, m_tiles = (count + 127) / 128;
