@@ -159,3 +159,29 @@ def test_assemble_latent_rows_matches_the_row_split():
             a, b = ray_block(Hf, r, world)
             bands[r, :, :b - a] = full[:, a:b]
         assert torch.equal(assemble_latent_rows(bands, Hf), full)
+
+
+def test_too_many_views_raise_before_anything_is_enqueued():
+    """the tensor-core path takes 2..4 input views (fp32: 2..8); a larger V must fail up front with a clear
+    message, not after K1 / K3 / K4 have been queued."""
+    import pytest
+    import torch
+    from mpsnerf_b200 import synthetic
+    from mpsnerf_b200.engine import RenderEngine
+    from mpsnerf_b200.lib import skinnning_batch as SB
+    from mpsnerf_b200.run_nerf_batch import _select
+    scene = synthetic.make_scene("thuman", seed=0, H=32, W=32, n_views=5)
+    SB.set_default_smpl_models(scene.smpl)
+    net = SB.SKinningBatch(human_sample=1, use_f2d=1, use_trans=1, smooth_loss=1, num_instances=2, mean_shape=0,
+                           correction_field=0, skinning_field=0, data_set_type="THuman_B", append_rgb=1, with_viewdirs=0)
+    sp, tp = _select(scene.sp_input, 0), _select(scene.tp_input, 0)
+    with pytest.raises(ValueError, match="input views"):
+        RenderEngine(net, precision="bf16").prepare_frame(sp, tp, net._smpl_for(sp["gender"]))
+
+
+def test_build_records_the_source_hash():
+    """a stale .so must not load silently -- the library carries the hash of the sources it was built from."""
+    from mpsnerf_b200 import build as B
+    assert B.is_current() and len(B.source_hash()) == 64
+    with open(B.HASH_FILE) as fh:
+        assert fh.read().strip() == B.source_hash()
