@@ -211,7 +211,7 @@ struct TArgs {
   int prof;
   const int32_t* count_dev;   // optional device-side active count (count is then the slab capacity)
   int64_t first;
-  int opt;                    // experiment switches (MPSNERF_T_OPT): bit 0 = partner dots as packed half2 FMAs instead of fp32
+  int opt;                    // experiment switches (MPSNERF_T_OPT): bit 0 = partner dots in fp32 instead of packed half2 FMAs
 };
 
 // LayerNorm over the 155 real columns of a row whose 160 columns are split between four threads
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
             // fp16 anyway; q is rounded to fp16 as well and the products run as packed half2 FMAs into eight short
             // partial sums (four products each, so the fp16 accumulation error stays ~2^-11 of a term), which are
             // added up in fp32 -- a third of the instructions of unpacking every key to fp32 first.
-            if (!(a.opt & 1)) {
+            if (a.opt & 1) {
 #pragma unroll
               for (int j = 1; j < V; ++j) {
                 const int rj = p0 + ((tok + j >= V) ? tok + j - V : tok + j);

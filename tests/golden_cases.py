@@ -20,8 +20,10 @@ CASES = {
     # stratified jitter on, white background composited in
     "opaque": dict(scenes=[dict(kind="thuman", seed=3, novel_pose=True)], n_rays=384, S=64, alpha_gain=300.0, alpha_bias=40.0,
                    perturb=True, white_bkgd=True),
-    # --occupancy 1 compositing variant
-    "occupancy": dict(scenes=[dict(kind="thuman", seed=4)], n_rays=256, S=64, alpha_gain=300.0, alpha_bias=0.0, occupancy=1),
+    # --occupancy 1 compositing variant.  There alpha = wide_sigmoid(raw_3) directly, without the x dist (~0.02) of the
+    # density form: a density head of gain 300 would be ~40x more sensitive than anything in density mode (a bf16-level
+    # error of 0.1 in raw_3 moves alpha by 0.025), so this case uses gain 60 -- raw_3 in -2 .. +3, still saturating
+    "occupancy": dict(scenes=[dict(kind="thuman", seed=4)], n_rays=256, S=64, alpha_gain=60.0, alpha_bias=0.0, occupancy=1),
     # H36M at its real size: 1000 x 1000 input views, latent 250 x 250
     "h36m_full": dict(scenes=[dict(kind="h36m", seed=6, novel_pose=True)], n_rays=256, S=64, alpha_gain=300.0),
     # B = 2 subjects in one call, genders 1 (male tables) and 0 (female tables)
