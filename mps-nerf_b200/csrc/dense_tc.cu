@@ -211,8 +211,7 @@ struct TArgs {
   int prof;
   const int32_t* count_dev;   // optional device-side active count (count is then the slab capacity)
   int64_t first;
-  int opt;                    // A/B switches (MPSNERF_T_OPT): bit 0 = partner dots in fp32 instead of packed half2 FMAs,
-                              // bit 1 = attention output repacked to bf16 instead of handed over as fp16
+  int opt;                    // experiment switches (MPSNERF_T_OPT): bit 0 = partner dots in fp32 instead of packed half2 FMAs
 };
 
 // LayerNorm over the 155 real columns of a row whose 160 columns are split between four threads
@@ -344,11 +343,9 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     auto done = [&]() { if (elect_one()) mma_commit(&pipe->d_bar[0]); __syncwarp(); ++g; };
     // A (TMEM, kSteps K=16 steps starting at column acol) x weight chunks with kN rows -> D column dcol.
     // One ring slot per 64 K columns: the barrier probe of a chunk hides behind the queued MMAs of the previous one.
-    auto gemm = [&](auto ksteps_c, auto n_c, uint32_t dcol, uint32_t acol, bool accumulate, bool a_f16 = false) {
+    auto gemm = [&](auto ksteps_c, auto n_c, uint32_t dcol, uint32_t acol, bool accumulate) {
       constexpr int kSteps = decltype(ksteps_c)::value, kN = decltype(n_c)::value;
-      // A operand in TMEM as bf16 pairs, or (attention output, MPSNERF_T_OPT bit 1 off) as fp16 pairs: kind::f16 takes
-      // the A and B formats independently, the weights stay bf16
-      const uint32_t idesc = a_f16 ? instr_desc_f16a(kN) : instr_desc_bf16(kN);
+      constexpr uint32_t idesc = instr_desc_bf16(kN);
 #pragma unroll
       for (int k0 = 0; k0 < kSteps; k0 += 4) {
         const uint64_t bdesc = smem_desc_sw128(Cn.acquire());
@@ -398,12 +395,11 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         wait_a(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // q|k|v of head 0 -> team A
         wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 1 -> team B
         wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // head 2 -> team A (waits in R while A finishes head 0)
-        const bool of16 = !(a.opt & 2);       // attention output handed over as fp16 (no fp16 -> fp32 -> bf16 repack)
-        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true, of16); commit_w(0);      // x += o_0 Wo_0^T
+        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true); commit_w(0);            // x += o_0 Wo_0^T
         wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 3 -> team B
-        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true, of16); commit_w(1); // x += o_1 Wo_1^T
-        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true, of16);                   // x += o_2 Wo_2^T
-        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true, of16);              // x += o_3 Wo_3^T
+        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true); commit_w(1);       // x += o_1 Wo_1^T
+        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                         // x += o_2 Wo_2^T
+        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);                    // x += o_3 Wo_3^T
         done();
         // Feed-forward, pipelined in two halves of the hidden layer: hidden columns [0,64) are handed to the
         // epilogue threads that own them (q < 2) while [64,128) is still being computed, and x += gelu(.) W2^T runs
@@ -650,13 +646,8 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
               }
             }
             uint32_t pk[16];
-            if (a.opt & 2) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(vh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
-            } else {             // o goes to the out-projection as it is: fp16 pairs (the MMA's A format for these GEMMs)
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = *reinterpret_cast<const uint32_t*>(&vh[i]);
-            }
+            for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(vh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
             if (hh == 1) { mbar_wait(&pipe->w_bar[team], pw & 1); ++pw; }     // (long complete by now)
             tmem_st_u16(tl + kT_ColO + 32 * team + 16 * hf, pk);
             tmem_st_wait();
