@@ -343,9 +343,11 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
     auto done = [&]() { if (elect_one()) mma_commit(&pipe->d_bar[0]); __syncwarp(); ++g; };
     // A (TMEM, kSteps K=16 steps starting at column acol) x weight chunks with kN rows -> D column dcol.
     // One ring slot per 64 K columns: the barrier probe of a chunk hides behind the queued MMAs of the previous one.
-    auto gemm = [&](auto ksteps_c, auto n_c, uint32_t dcol, uint32_t acol, bool accumulate) {
+    auto gemm = [&](auto ksteps_c, auto n_c, uint32_t dcol, uint32_t acol, bool accumulate, auto f16_c) {
       constexpr int kSteps = decltype(ksteps_c)::value, kN = decltype(n_c)::value;
-      constexpr uint32_t idesc = instr_desc_bf16(kN);
+      // operands bf16 x bf16, or fp16 x fp16 for the out-projection (its A operand, the attention output, is produced
+      // in fp16 and handed over without a repack; its weights are packed as fp16, pack.py)
+      constexpr uint32_t idesc = decltype(f16_c)::value ? instr_desc_f16(kN) : instr_desc_bf16(kN);
 #pragma unroll
       for (int k0 = 0; k0 < kSteps; k0 += 4) {
         const uint64_t bdesc = smem_desc_sw128(Cn.acquire());
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
       __syncwarp();
       Cn.advance();
     };
+    using BF = std::false_type; using F16 = std::true_type;
     using K10 = std::integral_constant<int, 10>; using K4 = std::integral_constant<int, 4>; using K8 = std::integral_constant<int, 8>;
     using N192 = std::integral_constant<int, 192>; using N160 = std::integral_constant<int, 160>; using N128 = std::integral_constant<int, 128>; using N64 = std::integral_constant<int, 64>;
     for (int64_t tbase = cid * kC; tbase < ntiles; tbase += ncl * kC) {
@@ -392,14 +395,14 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         auto wait_o = [&](int t) { pf.start(); mbar_wait(&pipe->o_bar[t], po[t] & 1); ++po[t]; pf.stop(acc_a); tc_fence_after(); };
         auto commit_q = [&](int t) { if (elect_one()) mma_commit(&pipe->q_bar[t]); __syncwarp(); };
         auto commit_w = [&](int t) { if (elect_one()) mma_commit(&pipe->w_bar[t]); __syncwarp(); };
-        wait_a(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // q|k|v of head 0 -> team A
-        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 1 -> team B
-        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(0);           // head 2 -> team A (waits in R while A finishes head 0)
-        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true); commit_w(0);            // x += o_0 Wo_0^T
-        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false); commit_q(1);           // head 3 -> team B
-        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true); commit_w(1);       // x += o_1 Wo_1^T
-        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);                         // x += o_2 Wo_2^T
-        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);                    // x += o_3 Wo_3^T
+        wait_a(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false, BF{}); commit_q(0);           // q|k|v of head 0 -> team A
+        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false, BF{}); commit_q(1);     // head 1 -> team B
+        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false, BF{}); commit_q(0);     // head 2 -> team A (waits in R while A finishes head 0)
+        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true, F16{}); commit_w(0);     // x += o_0 Wo_0^T
+        wait_r(); gemm(K10{}, N192{}, kT_ColR, kT_ColY, false, BF{}); commit_q(1);     // head 3 -> team B
+        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true, F16{}); commit_w(1); // x += o_1 Wo_1^T
+        wait_o(0); gemm(K4{}, N160{}, kT_ColX, kT_ColO, true, F16{});                  // x += o_2 Wo_2^T
+        wait_o(1); gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true, F16{});             // x += o_3 Wo_3^T
         done();
         // Feed-forward, pipelined in two halves of the hidden layer: hidden columns [0,64) are handed to the
         // epilogue threads that own them (q < 2) while [64,128) is still being computed, and x += gelu(.) W2^T runs
@@ -412,10 +415,10 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
         if (elect_one()) mma_commit(&pipe->h_bar[1]);
         __syncwarp();
         pf.start(); mbar_wait(&pipe->g_bar[0], pg & 1); pf.stop(acc_a); tc_fence_after();
-        gemm(K4{}, N160{}, kT_ColX, kT_ColO, true);
+        gemm(K4{}, N160{}, kT_ColX, kT_ColO, true, BF{});
         pf.start(); mbar_wait(&pipe->g_bar[1], pg & 1); pf.stop(acc_a); tc_fence_after();
         ++pg;
-        gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true);
+        gemm(K4{}, N160{}, kT_ColX, kT_ColO + 32, true, BF{});
         done();
       }
     }
@@ -645,9 +648,9 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
                 for (int i = 0; i < 4; ++i) vh[4 * u + i] = __hfma2(wj, h2[i], vh[4 * u + i]);
               }
             }
-            uint32_t pk[16];
+            uint32_t pk[16];         // o leaves as the fp16 pairs it was accumulated in: the out-projection is an fp16 GEMM
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(vh[i]); pk[i] = pack_bf16x2(f.x, f.y); }
+            for (int i = 0; i < 16; ++i) pk[i] = *reinterpret_cast<const uint32_t*>(&vh[i]);
             if (hh == 1) { mbar_wait(&pipe->w_bar[team], pw & 1); ++pw; }     // (long complete by now)
             tmem_st_u16(tl + kT_ColO + 32 * team + 16 * hf, pk);
             tmem_st_wait();

@@ -155,6 +155,12 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int N, int M = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with A = B = fp16, D = f32 (A and B must share their format: an fp16 A against a bf16 B is an illegal
+// instruction on sm_100a -- tried)
+__host__ __device__ constexpr uint32_t instr_desc_f16(int N, int M = 128) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {

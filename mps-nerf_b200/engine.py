@@ -39,7 +39,7 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def pack_kmajor_sw128(w, n_pad=None, k_pad=None):
+def pack_kmajor_sw128(w, n_pad=None, k_pad=None, dtype=torch.bfloat16):
     """Pack a (N,K) weight into the K-major SWIZZLE_128B chunk layout of csrc/umma.cuh.
 
     Returns a uint8 tensor of (K_pad/64) chunks x N_pad rows x 128 bytes: bf16, the 16-byte
@@ -49,8 +49,8 @@ def pack_kmajor_sw128(w, n_pad=None, k_pad=None):
     N, K = w.shape
     n_pad = n_pad or ((N + 15) // 16) * 16
     k_pad = k_pad or ((K + 63) // 64) * 64
-    wp = torch.zeros(n_pad, k_pad, dtype=torch.bfloat16, device=w.device)
-    wp[:N, :K] = w.to(torch.bfloat16)
+    wp = torch.zeros(n_pad, k_pad, dtype=dtype, device=w.device)      # bf16, or fp16 (the out-projection, see pack.py)
+    wp[:N, :K] = w.to(dtype)
     t = wp.reshape(n_pad, k_pad // 64, 8, 8)                       # (row, chunk, unit, elem)
     r7 = (torch.arange(n_pad, device=w.device) & 7)[:, None]
     src_unit = torch.arange(8, device=w.device)[None, :] ^ r7      # stored unit u holds logical unit u ^ r7

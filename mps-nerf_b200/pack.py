@@ -69,7 +69,10 @@ def pack_weights_bf16(net, device=None):
         # Wo_0, q|k|v of head 3, Wo_1, Wo_2, Wo_3
         for item in ("q0", "q1", "q2", "o0", "q3", "o1", "o2", "o3"):
             h = int(item[1])
-            parts.append(pack_kmajor_sw128(qkv[h], 192, 192) if item[0] == "q" else pack_kmajor_sw128(out[h], 160, 64))
+            # the out-projection runs as an fp16 x fp16 GEMM: its A operand, the attention output, is produced in fp16
+            # by the epilogue and handed over as it is (kind::f16 does not mix an fp16 A with a bf16 B)
+            parts.append(pack_kmajor_sw128(qkv[h], 192, 192) if item[0] == "q"
+                         else pack_kmajor_sw128(out[h], 160, 64, dtype=torch.float16))
         parts.append(pack_kmajor_sw128(w1[:64], 64, 192))       # the FF hidden layer is computed in two 64-row halves
         parts.append(pack_kmajor_sw128(w1[64:128], 64, 192))
         parts.append(pack_kmajor_sw128(w2, 160, 128))

@@ -342,7 +342,10 @@ def transformer(tok, sd, lin):
         q, k, v = (t.reshape(P, V, 4, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
         att = torch.softmax(torch.einsum("bhid,bhjd->bhij", q, k) * (64 ** -0.5), dim=-1)      # (attention itself stays fp32)
         o = torch.einsum("bhij,bhjd->bhid", att, v).permute(0, 2, 1, 3).reshape(P, V, 256)
-        x = x + lin(o, sd[p + "0.fn.fn.to_out.0.weight"], sd[p + "0.fn.fn.to_out.0.bias"])
+        if lin.bf16:    # the tensor-core path runs the out-projection as an fp16 x fp16 GEMM (o is produced in fp16)
+            x = x + F.linear(o.half().float(), sd[p + "0.fn.fn.to_out.0.weight"].half().float(), sd[p + "0.fn.fn.to_out.0.bias"])
+        else:
+            x = x + lin(o, sd[p + "0.fn.fn.to_out.0.weight"], sd[p + "0.fn.fn.to_out.0.bias"])
         h = F.gelu(_ln_linear(x, sd[p + "1.fn.norm.weight"], sd[p + "1.fn.norm.bias"], sd[p + "1.fn.fn.net.0.weight"],
                               sd[p + "1.fn.fn.net.0.bias"], lin))
         x = x + lin(h, sd[p + "1.fn.fn.net.3.weight"], sd[p + "1.fn.fn.net.3.bias"])
