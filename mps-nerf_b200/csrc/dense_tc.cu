@@ -192,10 +192,11 @@ constexpr uint32_t kT_PD = 32768;                  // partial q.k dots  float[2]
 constexpr uint32_t kT_TeamBytes = 36864;
 constexpr uint32_t kT_LS = 2 * kT_TeamBytes;       // LayerNorm partial sums float[2][4][128]
 constexpr uint32_t kT_RING = kT_LS + 4096;         // 1024-aligned: 2 * 36864 + 4096 = 77824 = 76 * 1024
-constexpr int kT_Slots = 5;
+constexpr int kT_Slots = 6;          // (5 until the LayerNorm vectors left shared memory: the tensor pipe waited ~9 % of a tile for weights)
+constexpr int kT_PendFloats = 5 * 160;   // the deferred-bias vectors kept in shared memory: pend_in / pend_mid of both layers, pend_out
 constexpr uint32_t kT_SlotBytes = kQkvChunk;
 constexpr uint32_t kT_FP = kT_RING + kT_Slots * kT_SlotBytes;
-constexpr uint32_t kT_PIPE = kT_FP + ((kTFloats * 4 + 15) / 16) * 16;
+constexpr uint32_t kT_PIPE = kT_FP + ((kT_PendFloats * 4 + 15) / 16) * 16;
 constexpr uint32_t kT_Smem = kT_PIPE + sizeof(Pipe);
 static_assert(kT_RING % 1024 == 0 && kT_SlotBytes % 1024 == 0, "ring slots must be 1024-byte aligned");
 static_assert(kT_Smem <= 232448 - 1024, "T kernel shared memory over budget");
@@ -303,7 +304,12 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
   if (warp == kFMmaWarp) { tmem_alloc(&pipe->tmem_base, 512); tmem_relinquish(); }
   {
     const float* src = reinterpret_cast<const float*>(a.blob + kFloatOff);
-    for (int i = tid; i < kTFloats; i += kFThreads) FP[i] = src[i];
+    // Only the deferred-bias vectors are needed on chip: the LayerNorm affine and the feed-forward bias live in the
+    // packed weights (pack.py).  FP[160 j ..]: j = 0 pend_in(l0), 1 pend_mid(l0), 2 pend_in(l1), 3 pend_mid(l1), 4 pend_out.
+    for (int i = tid; i < kT_PendFloats; i += kFThreads) {
+      const int j = i / 160, c = i - 160 * j;
+      FP[i] = src[j == 4 ? 2 * kTLayerFloats + c : (j >> 1) * kTLayerFloats + ((j & 1) ? 800 : 320) + c];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
       fetch_staged();
       float x[40];
       unpack_tokens(x);
-      ln_to_tmem(x, nullptr, FP, FP + 160, LS, r, q, warp, tl);
+      ln_to_tmem(x, nullptr, nullptr, nullptr, LS, r, q, warp, tl);
       hand_over();
     };
 
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
       const bool has_next = tbase + ncl * kC < ntiles;
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
-        const float* fp = FP + l * kTLayerFloats;   // ln1_g ln1_b pend_in ln2_g ln2_b pend_mid b1
+        const float* fp = FP + l * 320;             // pend_in, pend_mid of this layer
         {
           // ---- attention (lib/transformer.py:59-71).  Two teams of 8 warps (team = q >> 1: A = heads 0, 2;
           // B = heads 1, 3) work on different heads at the same time.  R = [q | k | v] of one head, 64 columns
@@ -667,7 +673,7 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
           pf.start();
           float x[40];
           load_x40(tl + kT_ColX + 40 * q, x);
-          ln_to_tmem(x, fp + 800, fp + 480, fp + 640, LS, r, q, warp, tl);
+          ln_to_tmem(x, fp + 160, nullptr, nullptr, LS, r, q, warp, tl);
           pf.stop(sec[5]);
           hand_over();
         }
@@ -706,14 +712,13 @@ __global__ void __launch_bounds__(kFThreads, 1) xformer_tc_kernel(const TArgs a_
           float x[40];
           load_x40(tl + kT_ColX + 40 * q, x);
           if (l == 0) {
-            const float* f1 = FP + kTLayerFloats;        // layer 1: LN1 on x + pend_in
-            ln_to_tmem(x, f1 + 320, f1, f1 + 160, LS, r, q, warp, tl);
+            ln_to_tmem(x, FP + 320, nullptr, nullptr, LS, r, q, warp, tl);      // layer 1: LN1 on x + pend_in
             pf.stop(sec[7]);
             hand_over();
           } else {
             if (valid && tok < 2) {
               // ---- output tokens 0 (density branch) and 1 (colour branch), lib/skinnning_batch.py:441-442
-              const float4* p4 = reinterpret_cast<const float4*>(FP + 2 * kTLayerFloats + 40 * q);
+              const float4* p4 = reinterpret_cast<const float4*>(FP + 640 + 40 * q);
               uint4* dst = reinterpret_cast<uint4*>((tok == 0 ? a.tok0 : a.tok1) + pnt * kTokLd + 40 * q);
 #pragma unroll
               for (int c = 0; c < 5; ++c) {
