@@ -6,9 +6,11 @@ This is the host side of the hot path.  Per ``render()`` call it
      (lib/skinnning_batch.py:206,243,266,289);
   2. runs the encoder trunk once and lays its output out NHWC -- the reference re-runs it
      per chunk (lib/skinnning_batch.py:350-351);
-  3. builds the two exact nearest-vertex grids (posed vertices in SMPL space, template);
-  4. launches K1 (sample + mask + argmin + compaction) over all rays, reads the active count
-     (the only host sync of a frame), then K3/K4/K5 over slabs of active points and K6.
+  3. builds the two exact nearest-vertex grids (posed vertices in SMPL space, template)
+     -- steps 1-3 as three CUDA-graph branches on three streams, K1 starting behind the first (DESIGN.md section 2);
+  4. enqueues K1 (sample + mask + argmin + compaction) over all rays, K3 / K4 / K5 for a slab of active points whose
+     count is read on the device, and K6 -- one C call (mpsnerf_render_rays_bf16) or stage by stage -- and looks at
+     the active count only afterwards (overflow beyond the slab: remainder slabs, K6 again).
 All per-point arithmetic happens in libmpsnerf_b200.so; torch is used for memory, streams
 and the cuDNN encoder trunk only.
 """
