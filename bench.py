@@ -515,7 +515,8 @@ def run_reference(a):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     world, workload, strong = resolve_mode(a)
-    cpu = cpu_baseline(budget_s=150.0, steps=a.steps, warmup=a.warmup, workload=workload)
+    cpu = cpu_baseline(budget_s=float(os.environ.get("MPSNERF_CPU_ARM_BUDGET_S", "150")), steps=a.steps, warmup=a.warmup,
+                       workload=workload)
     print(json.dumps({
         "impl": "reference", "metric": "rays/sec (render fwd)", "value": cpu["value"], "unit": "rays/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * cpu["seconds"] / a.steps,

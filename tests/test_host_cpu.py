@@ -185,3 +185,36 @@ def test_build_records_the_source_hash():
     assert B.is_current() and len(B.source_hash()) == 64
     with open(B.HASH_FILE) as fh:
         assert fh.read().strip() == B.source_hash()
+
+
+def test_bench_reference_arm_prints_the_contract_line(monkeypatch, capsys):
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the contract keys, the same `config` object
+    our arm prints, and `cpu_baseline.kind` = "reference" when a reference tree is present, "port" otherwise."""
+    import argparse
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from oracle import run_reference as RR
+    monkeypatch.setenv("MPSNERF_CPU_ARM_BUDGET_S", "2")
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    cwd = os.getcwd()
+    try:
+        bench.run_reference(argparse.Namespace(gpus=1, steps=1, warmup=0, workload=None, mode="auto"))
+    finally:
+        os.chdir(cwd)
+    line = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] > 0
+    assert d["config"] == bench.workload_config("thuman", 1, False)
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == ("reference" if RR.find_reference() else "port")
+    # N > 1: both arms name the strong-scaling workload (BASELINE configs[2])
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    a = argparse.Namespace(gpus=8, steps=1, warmup=0, workload=None, mode="auto")
+    assert bench.resolve_mode(a) == (8, "h36m", True)
