@@ -4,7 +4,10 @@
 // SKinningBatch.forward (lib/skinnning_batch.py:438-473) layer by layer with fp32 FMA
 // accumulation.  This is the high-precision mode (rgb within 1e-4 of the reference); the
 // production path is the bf16 tcgen05 kernel in dense_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace mps {
 
@@ -74,11 +77,255 @@ linear_f32_kernel(const float* __restrict__ X, int ldx, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ the same linear on the tensor cores, fp32-accurate
+// 3xTF32: every fp32 operand is split into a TF32 "hi" part and a TF32 "lo" remainder (x = hi + lo exactly to 2^-22
+// relative), and a product is formed as  a_lo b_hi + a_hi b_lo + a_hi b_hi  with fp32 accumulation in the tensor core
+// (mma.sync.m16n8k8, the warp-level path -- the operands live in registers, which is what makes the split cheap; the
+// dropped a_lo b_lo term is 2^-22 of the product).  Error ~1e-6 relative: the <= 1e-4 rgb bound of the high-precision
+// option holds with the same margin as on the CUDA cores (tests: fp32 goldens, dense train fwd / bwd), at 3 tensor-core
+// MMAs per product instead of one FMA per MAC.  Block tile 128 x 64 x 16, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32.
+constexpr int kTcPad = 8;      // row stride 136 / 72 floats: the fragment loads (8 t + g) hit 32 distinct banks
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float rem = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int ACT /*0 none, 1 relu, 2 gelu(erf)*/>
+__global__ void __launch_bounds__(kLinThreads)
+linear_tf32x3_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int K,
+                     const float* __restrict__ b, const float* Res, int ldr, float* Y,
+                     int ldy, int64_t M, int N) {
+  __shared__ float Xs[BK][BM + kTcPad];
+  __shared__ float Ws[BK][BN + kTcPad];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int e = tid; e < BM * BK; e += kLinThreads) {
+      const int kk = e % BK, mm = e / BK;
+      const int64_t m = m0 + mm;
+      const int k = k0 + kk;
+      Xs[kk][mm] = (m < M && k < K) ? X[m * ldx + k] : 0.f;
+    }
+    for (int e = tid; e < BN * BK; e += kLinThreads) {
+      const int kk = e % BK, nn = e / BK;
+      const int n = n0 + nn, k = k0 + kk;
+      Ws[kk][nn] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = wm * 32 + mt * 16 + g;
+        split_tf32(Xs[ks + t][row], ah[mt][0], al[mt][0]);
+        split_tf32(Xs[ks + t][row + 8], ah[mt][1], al[mt][1]);
+        split_tf32(Xs[ks + t + 4][row], ah[mt][2], al[mt][2]);
+        split_tf32(Xs[ks + t + 4][row + 8], ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = wn * 32 + nt * 8 + g;
+        split_tf32(Ws[ks + t][col], bh[nt][0], bl[nt][0]);
+        split_tf32(Ws[ks + t + 4][col], bh[nt][1], bl[nt][1]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma_tf32(acc[mt][nt], al[mt], bh[nt]);      // the small terms first
+          mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+          mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t m = m0 + wm * 32 + mt * 16 + g + ((e & 2) ? 8 : 0);
+        const int n = n0 + wn * 32 + nt * 8 + 2 * t + (e & 1);
+        if (m >= M || n >= N) continue;
+        float v = acc[mt][nt][e] + (b ? b[n] : 0.f);
+        if (ACT == 1) v = fmaxf(v, 0.f);
+        if (ACT == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        if (Res) v += Res[m * ldr + n];
+        Y[m * ldy + n] = v;
+      }
+}
+
+// ------------------------------------------------------------------ the same 3xTF32 linear on the tcgen05 tensor cores
+// Tile = 128 rows x kN outputs, K in chunks of 32 (one 128-byte SWIZZLE_128B row per operand row).  Every chunk is
+// staged in shared memory four times over -- A_hi, A_lo, B_hi, B_lo, hi = the value truncated to TF32, lo = the exact
+// remainder -- by a coalesced cooperative load (a warp reads one row's 128 bytes per instruction), and one thread issues
+// 4 K-steps x 3 MMAs (lo.hi, hi.lo, hi.hi; kind::tf32, SS form, fp32 accumulator in tensor memory).  Two stages:
+// the loads of chunk c + 1 run under the MMAs of chunk c; a stage is reused when the commit of the MMAs that read
+// it has arrived.  Epilogue: thread = row (TMEM lane), tcgen05.ld 16 columns at a time -> bias / activation /
+// residual -> global.  This is a plain tiled GEMM, not a fused kernel: the high-precision option is the
+// validation / training arithmetic, launched layer by layer.
+constexpr int kGRows = 128, kGChunk = 32, kGThreads = 512;      // 16 warps stage the operands, warps 0-3 drain TMEM
+template <int kN> __host__ __device__ constexpr uint32_t g_stage_bytes() { return 2u * 128u * 128u + 2u * (uint32_t)kN * 128u; }
+
+__device__ __forceinline__ uint32_t sw128_f32_off(int r, int k) {      // byte offset of element (row r, K index k < 32)
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7))) << 4) + (k & 3) * 4);
+}
+
+template <int ACT, int kN>
+__global__ void __launch_bounds__(kGThreads, 1)
+linear_tcgen05_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int K,
+                      const float* __restrict__ b, const float* Res, int ldr, float* Y, int ldy, int64_t M, int N) {
+  using namespace umma;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t kA = 128u * 128u, kB = (uint32_t)kN * 128u, kStage = g_stage_bytes<kN>();
+  if (warp == 0) { tmem_alloc(&tmem_base_s, kN); tmem_relinquish(); }
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  const int64_t m0 = (int64_t)blockIdx.x * kGRows;
+  const int n0 = blockIdx.y * kN;
+  const int nchunks = (K + kGChunk - 1) / kGChunk;
+  constexpr uint32_t idesc = instr_desc_tf32(kN);
+  uint32_t ph[2] = {0u, 0u};
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1;
+    if (c >= 2) { mbar_wait(&bar[s], ph[s]); ph[s] ^= 1u; }      // the MMAs of chunk c - 2 have read stage s
+    uint8_t* st = smem + (size_t)s * kStage;
+    const int k0 = c * kGChunk;
+    for (int e = tid; e < kGRows * kGChunk; e += kGThreads) {      // A: rows of X
+      const int kk = e & 31, rr = e >> 5;
+      const int64_t m = m0 + rr;
+      const int k = k0 + kk;
+      const float v = (m < M && k < K) ? X[m * ldx + k] : 0.f;
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      const uint32_t off = sw128_f32_off(rr, kk);
+      *reinterpret_cast<float*>(st + off) = hi;
+      *reinterpret_cast<float*>(st + kA + off) = v - hi;
+    }
+    for (int e = tid; e < kN * kGChunk; e += kGThreads) {          // B: rows of W (nn.Linear layout: (N, K), K-major)
+      const int kk = e & 31, rr = e >> 5;
+      const int n = n0 + rr, k = k0 + kk;
+      const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      const uint32_t off = sw128_f32_off(rr, kk);
+      *reinterpret_cast<float*>(st + 2 * kA + off) = hi;
+      *reinterpret_cast<float*>(st + 2 * kA + kB + off) = v - hi;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + kA, b_hi = a_hi + 2 * kA, b_lo = b_hi + kB;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const uint64_t dah = smem_desc_sw128(a_hi + k4 * 32), dal = smem_desc_sw128(a_lo + k4 * 32);
+        const uint64_t dbh = smem_desc_sw128(b_hi + k4 * 32), dbl = smem_desc_sw128(b_lo + k4 * 32);
+        mma_tf32_ss(tm, dal, dbh, idesc, (c | k4) ? 1u : 0u);       // the small terms first
+        mma_tf32_ss(tm, dah, dbl, idesc, 1u);
+        mma_tf32_ss(tm, dah, dbh, idesc, 1u);
+      }
+      mma_commit(&bar[s]);
+    }
+  }
+  {
+    const int s = (nchunks - 1) & 1;       // commits arrive in issue order: the last one covers every MMA
+    mbar_wait(&bar[s], ph[s]);
+  }
+  tc_fence_after();
+  // Epilogue.  A thread owns a row (its TMEM lane); writing rows straight to global would scatter every store
+  // instruction over 32 rows, so the tile goes through shared memory (the operand stages are free: every MMA has
+  // completed) and leaves with coalesced stores, bias / activation / residual applied on the way out.
+  float* tile = reinterpret_cast<float*>(smem);              // [128][kN + 1]
+  if (warp < 4) {                                            // warps 0-3 own the four TMEM lane quarters
+    for (int cb = 0; cb < kN; cb += 16) {
+      float v[16];
+      tmem_ld_x16(tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tile[tid * (kN + 1) + cb + i] = v[i];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < kGRows * kN; e += kGThreads) {
+    const int rr = e / kN, cc = e - rr * kN;
+    const int64_t m = m0 + rr;
+    const int n = n0 + cc;
+    if (m >= M || n >= N) continue;
+    float y = tile[rr * (kN + 1) + cc] + (b ? b[n] : 0.f);
+    if (ACT == 1) y = fmaxf(y, 0.f);
+    if (ACT == 2) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+    if (Res) y += Res[m * ldr + n];
+    Y[m * ldy + n] = y;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, kN);
+}
+
+// MPSNERF_FP32_GEMM = tcgen05 (default: 3xTF32, kind::tf32 tcgen05 tiles) | mma (3xTF32, warp-level mma.sync) |
+// simt (plain fp32 FMAs on the CUDA cores)
+static int fp32_gemm_mode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("MPSNERF_FP32_GEMM"); mode = !e ? 2 : (e[0] == 's' ? 0 : (e[0] == 'm' ? 1 : 2)); }
+  return mode;
+}
+
 template <int ACT>
 static int launch_linear(const float* X, int ldx, const float* W, int K, const float* b, const float* Res, int ldr,
                          float* Y, int ldy, int64_t M, int N, cudaStream_t st) {
+  const int mode = fp32_gemm_mode();
+  if (mode == 2 && N >= 32) {      // (the 1- and 3-wide heads stay on the warp-level path)
+    if (N > 128) {                 // wide layers: 256 outputs per tile, the activation rows are staged half as often
+      constexpr int kN = 256;
+      const size_t smem = 2 * (size_t)g_stage_bytes<kN>();
+      cudaFuncSetAttribute(linear_tcgen05_kernel<ACT, kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      dim3 grid((unsigned)((M + kGRows - 1) / kGRows), (unsigned)((N + kN - 1) / kN));
+      linear_tcgen05_kernel<ACT, kN><<<grid, kGThreads, smem, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
+    } else if (N > 64) {
+      constexpr int kN = 128;
+      const size_t smem = 2 * (size_t)g_stage_bytes<kN>();
+      cudaFuncSetAttribute(linear_tcgen05_kernel<ACT, kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      dim3 grid((unsigned)((M + kGRows - 1) / kGRows), (unsigned)((N + kN - 1) / kN));
+      linear_tcgen05_kernel<ACT, kN><<<grid, kGThreads, smem, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
+    } else {
+      constexpr int kN = 64;
+      const size_t smem = 2 * (size_t)g_stage_bytes<kN>();
+      cudaFuncSetAttribute(linear_tcgen05_kernel<ACT, kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      dim3 grid((unsigned)((M + kGRows - 1) / kGRows), (unsigned)((N + kN - 1) / kN));
+      linear_tcgen05_kernel<ACT, kN><<<grid, kGThreads, smem, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
+    }
+    return 0;
+  }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-  linear_f32_kernel<ACT><<<grid, kLinThreads, 0, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
+  if (mode >= 1)
+    linear_tf32x3_kernel<ACT><<<grid, kLinThreads, 0, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
+  else
+    linear_f32_kernel<ACT><<<grid, kLinThreads, 0, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
   return 0;
 }
 
@@ -104,30 +351,43 @@ __global__ void ln_rows_kernel(const float* __restrict__ X, int ldx, const float
 
 // ------------------------------------------------------------------ 4-head attention over the V view tokens
 // QKV (count*V, 768): [q(256) | k(256) | v(256)], head h = columns h*64..h*64+63 of each part
-// ('b n (h d) -> b h n d', lib/transformer.py:62).  One thread per (point, head, query token).
-__global__ void attention_kernel(const float* __restrict__ QKV, float* __restrict__ O, int64_t count, int V) {
-  const int64_t total = count * 4 * V;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(t % V);
-    const int h = (int)((t / V) % 4);
-    const int64_t p = t / (4 * V);
-    const float* q = QKV + (p * V + i) * 768 + h * 64;
-    float dots[MPSNERF_MAX_VIEWS];
-    float mx = -1e30f;
-    for (int j = 0; j < V; ++j) {
-      const float* k = QKV + (p * V + j) * 768 + 256 + h * 64;
-      float d = 0.f;
-      for (int c = 0; c < 64; ++c) d = fmaf(q[c], k[c], d);
-      dots[j] = d * 0.125f;                       // dim_head ** -0.5
-      mx = fmaxf(mx, dots[j]);
-    }
-    float den = 0.f;
-    for (int j = 0; j < V; ++j) { dots[j] = expf(dots[j] - mx); den += dots[j]; }
-    float* o = O + (p * V + i) * 256 + h * 64;
-    for (int c = 0; c < 64; ++c) {
-      float a = 0.f;
-      for (int j = 0; j < V; ++j) a = fmaf(dots[j] / den, QKV[(p * V + j) * 768 + 512 + h * 64 + c], a);
-      o[c] = a;
+// ('b n (h d) -> b h n d', lib/transformer.py:62).  One warp per point: lane l serves head l / 8 with the eight head
+// dims 8 (l % 8) .. -- every load and store is a coalesced 128-bit access of a 1 KB row part, the q.k dots are reduced
+// over the eight lanes of a head with three shuffle steps.  (Round 1 ran one thread per (point, head, query) over
+// 768-float-strided rows: 17 ms of a 128 ms fp32 frame.)
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ QKV, float* __restrict__ O, int64_t count, int V) {
+  const int lane = threadIdx.x & 31, h = lane >> 3, sub = lane & 7;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int col = h * 64 + 8 * sub;
+  for (int64_t p = w0; p < count; p += nw) {
+    const float* base = QKV + p * V * 768 + col;
+    for (int i = 0; i < V; ++i) {
+      const float4 qa = *reinterpret_cast<const float4*>(base + i * 768), qb = *reinterpret_cast<const float4*>(base + i * 768 + 4);
+      float dots[MPSNERF_MAX_VIEWS];
+      float mx = -1e30f;
+      for (int j = 0; j < V; ++j) {
+        const float4 ka = *reinterpret_cast<const float4*>(base + j * 768 + 256), kb = *reinterpret_cast<const float4*>(base + j * 768 + 260);
+        float d = qa.x * ka.x;
+        d = fmaf(qa.y, ka.y, d); d = fmaf(qa.z, ka.z, d); d = fmaf(qa.w, ka.w, d);
+        d = fmaf(qb.x, kb.x, d); d = fmaf(qb.y, kb.y, d); d = fmaf(qb.z, kb.z, d); d = fmaf(qb.w, kb.w, d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        dots[j] = d * 0.125f;                       // dim_head ** -0.5
+        mx = fmaxf(mx, dots[j]);
+      }
+      float den = 0.f;
+      for (int j = 0; j < V; ++j) { dots[j] = expf(dots[j] - mx); den += dots[j]; }
+      float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+      for (int j = 0; j < V; ++j) {
+        const float w = dots[j] / den;
+        const float4 va = *reinterpret_cast<const float4*>(base + j * 768 + 512), vb = *reinterpret_cast<const float4*>(base + j * 768 + 516);
+        oa.x = fmaf(w, va.x, oa.x); oa.y = fmaf(w, va.y, oa.y); oa.z = fmaf(w, va.z, oa.z); oa.w = fmaf(w, va.w, oa.w);
+        ob.x = fmaf(w, vb.x, ob.x); ob.y = fmaf(w, vb.y, ob.y); ob.z = fmaf(w, vb.z, ob.z); ob.w = fmaf(w, vb.w, ob.w);
+      }
+      float* o = O + (p * V + i) * 256 + col;
+      *reinterpret_cast<float4*>(o) = oa;
+      *reinterpret_cast<float4*>(o + 4) = ob;
     }
   }
 }
@@ -222,7 +482,7 @@ extern "C" int mpsnerf_dense_fp32(const float* tokens, int32_t ld, const float* 
     const float* const* P = L + 11 * l;   // ln1_w ln1_b qkv_w out_w out_b ln2_w ln2_b ff1_w ff1_b ff2_w ff2_b
     ln_rows_kernel<<<blocks_for(M3 * 32, 256), 256, 0, st>>>(w.X, 155, P[0], P[1], w.Y, 155, M3, 155);
     launch_linear<0>(w.Y, 155, P[2], 155, nullptr, nullptr, 0, w.QKV, 768, M3, 768, st);
-    attention_kernel<<<blocks_for(count * 4 * V, 128), 128, 0, st>>>(w.QKV, w.O, count, V);
+    attention_kernel<<<blocks_for(count * 32, 256), 256, 0, st>>>(w.QKV, w.O, count, V);
     launch_linear<0>(w.O, 256, P[3], 256, P[4], w.X, 155, w.X, 155, M3, 155, st);       // x += out(o)
     ln_rows_kernel<<<blocks_for(M3 * 32, 256), 256, 0, st>>>(w.X, 155, P[5], P[6], w.Y, 155, M3, 155);
     launch_linear<2>(w.Y, 155, P[7], 155, P[8], nullptr, 0, w.Hff, 128, M3, 128, st);
@@ -543,7 +803,7 @@ extern "C" int mpsnerf_dense_train_fwd(const float* tokens, int32_t ld, const fl
     const float* const* P = L + 11 * l;   // ln1_w ln1_b qkv_w out_w out_b ln2_w ln2_b ff1_w ff1_b ff2_w ff2_b
     ln_rows_kernel<<<blocks_for(M3 * 32, 256), 256, 0, st>>>(w.X[l], 155, P[0], P[1], w.Y1[l], 155, M3, 155);
     launch_linear<0>(w.Y1[l], 155, P[2], 155, nullptr, nullptr, 0, w.QKV[l], 768, M3, 768, st);
-    attention_kernel<<<blocks_for(count * 4 * V, 128), 128, 0, st>>>(w.QKV[l], w.O[l], count, V);
+    attention_kernel<<<blocks_for(count * 32, 256), 256, 0, st>>>(w.QKV[l], w.O[l], count, V);
     launch_linear<0>(w.O[l], 256, P[3], 256, P[4], w.X[l], 155, w.Xmid[l], 155, M3, 155, st);
     ln_rows_kernel<<<blocks_for(M3 * 32, 256), 256, 0, st>>>(w.Xmid[l], 155, P[5], P[6], w.Y2[l], 155, M3, 155);
     launch_linear<0>(w.Y2[l], 155, P[7], 155, P[8], nullptr, 0, w.Z[l], 128, M3, 128, st);
