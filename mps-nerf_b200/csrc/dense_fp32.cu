@@ -217,24 +217,31 @@ linear_tcgen05_kernel(const float* __restrict__ X, int ldx, const float* __restr
     if (c >= 2) { mbar_wait(&bar[s], ph[s]); ph[s] ^= 1u; }      // the MMAs of chunk c - 2 have read stage s
     uint8_t* st = smem + (size_t)s * kStage;
     const int k0 = c * kGChunk;
-    for (int e = tid; e < kGRows * kGChunk; e += kGThreads) {      // A: rows of X
-      const int kk = e & 31, rr = e >> 5;
-      const int64_t m = m0 + rr;
-      const int k = k0 + kk;
-      const float v = (m < M && k < K) ? X[m * ldx + k] : 0.f;
-      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-      const uint32_t off = sw128_f32_off(rr, kk);
-      *reinterpret_cast<float*>(st + off) = hi;
-      *reinterpret_cast<float*>(st + kA + off) = v - hi;
+    // Thread (kk = tid & 31, r0 = tid >> 5) stages column kk of rows r0, r0 + 16, ...: a warp reads 128 contiguous
+    // bytes of one row per load, and because 16 is a multiple of the 8-row swizzle period the shared-memory offset of a
+    // thread's elements advances by a constant 2048 bytes -- no per-element address arithmetic, 8 loads in flight.
+    const int kk = tid & 31, r0 = tid >> 5;
+    const int k = k0 + kk;
+    const uint32_t sw = sw128_f32_off(r0, kk);
+    {
+      const float* xp = X + (m0 + r0) * ldx + k;
+#pragma unroll
+      for (int i = 0; i < kGRows / 16; ++i) {                        // A: rows of X
+        const float v = (m0 + r0 + 16 * i < M && k < K) ? xp[(int64_t)(16 * i) * ldx] : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        *reinterpret_cast<float*>(st + sw + 2048u * i) = hi;
+        *reinterpret_cast<float*>(st + kA + sw + 2048u * i) = v - hi;
+      }
     }
-    for (int e = tid; e < kN * kGChunk; e += kGThreads) {          // B: rows of W (nn.Linear layout: (N, K), K-major)
-      const int kk = e & 31, rr = e >> 5;
-      const int n = n0 + rr, k = k0 + kk;
-      const float v = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
-      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-      const uint32_t off = sw128_f32_off(rr, kk);
-      *reinterpret_cast<float*>(st + 2 * kA + off) = hi;
-      *reinterpret_cast<float*>(st + 2 * kA + kB + off) = v - hi;
+    {
+      const float* wp = W + (size_t)(n0 + r0) * K + k;
+#pragma unroll
+      for (int i = 0; i < kN / 16; ++i) {                            // B: rows of W (nn.Linear layout: (N, K), K-major)
+        const float v = (n0 + r0 + 16 * i < N && k < K) ? wp[(size_t)(16 * i) * K] : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        *reinterpret_cast<float*>(st + 2 * kA + sw + 2048u * i) = hi;
+        *reinterpret_cast<float*>(st + 2 * kA + kB + sw + 2048u * i) = v - hi;
+      }
     }
     fence_proxy_async();
     __syncthreads();
