@@ -201,7 +201,8 @@ linear_tcgen05_kernel(const float* __restrict__ X, int ldx, const float* __restr
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr uint32_t kA = 128u * 128u, kB = (uint32_t)kN * 128u, kStage = g_stage_bytes<kN>();
-  if (warp == 0) { tmem_alloc(&tmem_base_s, kN); tmem_relinquish(); }
+  constexpr uint32_t kCols = kN <= 64 ? 64u : (kN <= 128 ? 128u : 256u);      // TMEM allocations are powers of two
+  if (warp == 0) { tmem_alloc(&tmem_base_s, kCols); tmem_relinquish(); }
   if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   tc_fence_before();
   __syncthreads();
@@ -212,37 +213,43 @@ linear_tcgen05_kernel(const float* __restrict__ X, int ldx, const float* __restr
   const int nchunks = (K + kGChunk - 1) / kGChunk;
   constexpr uint32_t idesc = instr_desc_tf32(kN);
   uint32_t ph[2] = {0u, 0u};
+  // Thread (kk = tid & 31, r0 = tid >> 5) stages column kk of rows r0, r0 + 16, ...: a warp reads 128 contiguous
+  // bytes of one row per load, and because 16 is a multiple of the 8-row swizzle period the shared-memory offset of a
+  // thread's elements advances by a constant 2048 bytes -- no per-element address arithmetic.  The loads of chunk
+  // c + 1 are issued into registers before the barrier that releases the MMAs of chunk c, so the global-memory
+  // latency runs under those MMAs instead of in front of them.
+  const int kk = tid & 31, r0 = tid >> 5;
+  const uint32_t sw = sw128_f32_off(r0, kk);
+  float ra[kGRows / 16], rb[kN / 16];
+  auto fetch = [&](int c) {
+    const int k = c * kGChunk + kk;
+    const float* xp = X + (m0 + r0) * ldx + k;
+#pragma unroll
+    for (int i = 0; i < kGRows / 16; ++i)                            // A: rows of X
+      ra[i] = (m0 + r0 + 16 * i < M && k < K) ? xp[(int64_t)(16 * i) * ldx] : 0.f;
+    const float* wp = W + (size_t)(n0 + r0) * K + k;
+#pragma unroll
+    for (int i = 0; i < kN / 16; ++i)                                // B: rows of W (nn.Linear layout: (N, K), K-major)
+      rb[i] = (n0 + r0 + 16 * i < N && k < K) ? wp[(size_t)(16 * i) * K] : 0.f;
+  };
+  fetch(0);
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
     if (c >= 2) { mbar_wait(&bar[s], ph[s]); ph[s] ^= 1u; }      // the MMAs of chunk c - 2 have read stage s
     uint8_t* st = smem + (size_t)s * kStage;
-    const int k0 = c * kGChunk;
-    // Thread (kk = tid & 31, r0 = tid >> 5) stages column kk of rows r0, r0 + 16, ...: a warp reads 128 contiguous
-    // bytes of one row per load, and because 16 is a multiple of the 8-row swizzle period the shared-memory offset of a
-    // thread's elements advances by a constant 2048 bytes -- no per-element address arithmetic, 8 loads in flight.
-    const int kk = tid & 31, r0 = tid >> 5;
-    const int k = k0 + kk;
-    const uint32_t sw = sw128_f32_off(r0, kk);
-    {
-      const float* xp = X + (m0 + r0) * ldx + k;
 #pragma unroll
-      for (int i = 0; i < kGRows / 16; ++i) {                        // A: rows of X
-        const float v = (m0 + r0 + 16 * i < M && k < K) ? xp[(int64_t)(16 * i) * ldx] : 0.f;
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        *reinterpret_cast<float*>(st + sw + 2048u * i) = hi;
-        *reinterpret_cast<float*>(st + kA + sw + 2048u * i) = v - hi;
-      }
+    for (int i = 0; i < kGRows / 16; ++i) {
+      const float hi = __uint_as_float(__float_as_uint(ra[i]) & 0xffffe000u);
+      *reinterpret_cast<float*>(st + sw + 2048u * i) = hi;
+      *reinterpret_cast<float*>(st + kA + sw + 2048u * i) = ra[i] - hi;
     }
-    {
-      const float* wp = W + (size_t)(n0 + r0) * K + k;
 #pragma unroll
-      for (int i = 0; i < kN / 16; ++i) {                            // B: rows of W (nn.Linear layout: (N, K), K-major)
-        const float v = (n0 + r0 + 16 * i < N && k < K) ? wp[(size_t)(16 * i) * K] : 0.f;
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        *reinterpret_cast<float*>(st + 2 * kA + sw + 2048u * i) = hi;
-        *reinterpret_cast<float*>(st + 2 * kA + kB + sw + 2048u * i) = v - hi;
-      }
+    for (int i = 0; i < kN / 16; ++i) {
+      const float hi = __uint_as_float(__float_as_uint(rb[i]) & 0xffffe000u);
+      *reinterpret_cast<float*>(st + 2 * kA + sw + 2048u * i) = hi;
+      *reinterpret_cast<float*>(st + 2 * kA + kB + sw + 2048u * i) = rb[i] - hi;
     }
+    if (c + 1 < nchunks) fetch(c + 1);
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -278,20 +285,29 @@ linear_tcgen05_kernel(const float* __restrict__ X, int ldx, const float* __restr
     }
   }
   __syncthreads();
-  for (int e = tid; e < kGRows * kN; e += kGThreads) {
-    const int rr = e / kN, cc = e - rr * kN;
-    const int64_t m = m0 + rr;
-    const int n = n0 + cc;
-    if (m >= M || n >= N) continue;
-    float y = tile[rr * (kN + 1) + cc] + (b ? b[n] : 0.f);
-    if (ACT == 1) y = fmaxf(y, 0.f);
-    if (ACT == 2) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
-    if (Res) y += Res[m * ldr + n];
-    Y[m * ldy + n] = y;
+  constexpr int kBatch = 8;      // residual loads of 8 elements in flight per thread before the first store
+  for (int e0 = tid; e0 < kGRows * kN; e0 += kGThreads * kBatch) {
+    float res[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int e = e0 + j * kGThreads, rr = e / kN, cc = e - rr * kN;
+      const bool ok = e < kGRows * kN && m0 + rr < M && n0 + cc < N;
+      res[j] = (ok && Res) ? Res[(m0 + rr) * ldr + n0 + cc] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int e = e0 + j * kGThreads, rr = e / kN, cc = e - rr * kN;
+      const int n = n0 + cc;
+      if (e >= kGRows * kN || m0 + rr >= M || n >= N) continue;
+      float y = tile[rr * (kN + 1) + cc] + (b ? b[n] : 0.f);
+      if (ACT == 1) y = fmaxf(y, 0.f);
+      if (ACT == 2) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+      Y[(m0 + rr) * ldy + n] = y + res[j];
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, kN);
+  if (warp == 0) tmem_dealloc(tm, kCols);
 }
 
 // MPSNERF_FP32_GEMM = tcgen05 (default: 3xTF32, kind::tf32 tcgen05 tiles) | mma (3xTF32, warp-level mma.sync) |
@@ -307,8 +323,14 @@ static int launch_linear(const float* X, int ldx, const float* W, int K, const f
                          float* Y, int ldy, int64_t M, int N, cudaStream_t st) {
   const int mode = fp32_gemm_mode();
   if (mode == 2 && N >= 32) {      // (the 1- and 3-wide heads stay on the warp-level path)
-    if (N > 128) {                 // wide layers: 256 outputs per tile, the activation rows are staged half as often
+    if (N > 160) {                 // wide layers: 256 outputs per tile, the activation rows are staged half as often
       constexpr int kN = 256;
+      const size_t smem = 2 * (size_t)g_stage_bytes<kN>();
+      cudaFuncSetAttribute(linear_tcgen05_kernel<ACT, kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      dim3 grid((unsigned)((M + kGRows - 1) / kGRows), (unsigned)((N + kN - 1) / kN));
+      linear_tcgen05_kernel<ACT, kN><<<grid, kGThreads, smem, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
+    } else if (N > 128) {          // the 155-wide token layers (to_out, net.3): one 160-column tile
+      constexpr int kN = 160;
       const size_t smem = 2 * (size_t)g_stage_bytes<kN>();
       cudaFuncSetAttribute(linear_tcgen05_kernel<ACT, kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       dim3 grid((unsigned)((M + kGRows - 1) / kGRows), (unsigned)((N + kN - 1) / kN));
