@@ -104,24 +104,26 @@ def raw2outputs(raw, z_vals, rays_d, white_bkgd=False):
 
 
 def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, perturb=0.0, N_importance=0,
-                network_fine=None, white_bkgd=False, sp_input=None, tp_input=None, perturb_u=None, _rays_ready=None):
+                network_fine=None, white_bkgd=False, sp_input=None, tp_input=None, perturb_u=None, _rays_ready=None,
+                smooth_delta=None):
     """ref :401-444.  ray_batch (B,C,8|11) = [o, d, near, far(, viewdirs)] -> dict of outputs.
 
     ``perturb_u`` (B,C,S) optionally supplies the stratified-sampling uniforms (otherwise drawn
-    with torch.rand on the device, as the reference draws them from the global RNG).
+    with torch.rand on the device, as the reference draws them from the global RNG); ``smooth_delta`` (B,C*S,3)
+    likewise supplies the perturbation of the smooth-loss second pass (ref :64, N(0, 0.01) otherwise).
     """
     net = _net_of(network_fn)
     if net.training and torch.is_grad_enabled():
         # training step (BASELINE config 4): forward with saved intermediates + hand-written backward, train.py
-        if global_args.smooth_loss and sp_input is not None and "smooth_interval" in sp_input and "global_step" in sp_input \
-                and int(sp_input["global_step"].reshape(-1)[0]) % int(sp_input["smooth_interval"].reshape(-1)[0]) == 0:
-            raise NotImplementedError("smooth-loss step (normals by double backward, ref :60-79) is not built: "
-                                      "train with --smooth_loss 0 or skip the interval steps")
+        # every smooth_interval-th step adds the normal-smoothness terms (ref :60-79): mps-nerf_b200/smooth.py
+        smooth_step = bool(global_args.smooth_loss) and bool(getattr(net, "smooth_loss", False)) and sp_input is not None \
+            and "smooth_interval" in sp_input and "global_step" in sp_input \
+            and int(sp_input["global_step"].reshape(-1)[0]) % int(sp_input["smooth_interval"].reshape(-1)[0]) == 0
         from .train import render_rays_train
         if _rays_ready is not None:
             torch.cuda.current_stream(ray_batch.device).wait_event(_rays_ready)
         return render_rays_train(net, ray_batch, sp_input, tp_input, N_samples, perturb, perturb_u, white_bkgd,
-                                 bool(global_args.occupancy), _select)
+                                 bool(global_args.occupancy), _select, smooth_step=smooth_step, smooth_delta=smooth_delta)
     B, C = ray_batch.shape[:2]
     dev = ray_batch.device
     S = int(N_samples)
@@ -163,6 +165,8 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, pert
 _COPY_STREAMS = {}
 # what the render path reads from the input dicts (engine._prepare_frame, lib/skinnning_batch.frame_context)
 HOT_KEYS_SP = ("gender", "params", "t_vertices", "img_all", "K_all", "R_all", "T_all")
+# the training loop's step counters (ref :541-542): passed through on the host, they decide which path a step takes
+STEP_KEYS = ("global_step", "smooth_interval")
 HOT_KEYS_TP = ("gender", "params", "vertices")
 
 
@@ -177,7 +181,9 @@ def _upload_hot(d, keys, dev):
         return v
     # gender stays on the host: it only selects which SMPL tables to use, a host-side decision; so do pinned source
     # views: the engine uploads them on its trunk stream, beside the front and K1 (engine._prepare_frame)
-    keep = lambda k, v: k == "gender" or (k == "img_all" and torch.is_tensor(v) and v.is_pinned())
+    # (global_step / smooth_interval likewise: the training loop's step counters decide on the host which path runs)
+    keep = lambda k, v: k in ("gender", "global_step", "smooth_interval") or \
+        (k == "img_all" and torch.is_tensor(v) and v.is_pinned())
     return {k: (d[k] if keep(k, d[k]) else mv(d[k])) for k in keys if k in d}
 
 
@@ -202,9 +208,15 @@ def batchify_rays(rays_flat, chunk=1024 * 32, sp_input=None, tp_input=None, **kw
     """ref :85-97: render in chunks of ``chunk`` rays and concatenate along the ray dim."""
     all_ret = {}
     pu = kwargs.pop("perturb_u", None)          # supplied stratified-sampling uniforms follow their rays
+    sd = kwargs.pop("smooth_delta", None)       # ... and so does a supplied smooth-loss perturbation (per sample point)
+    S = int(kwargs.get("N_samples", 64))
     for i in range(0, rays_flat.shape[1], chunk):
         ret = render_rays(rays_flat[:, i:i + chunk], sp_input=sp_input, tp_input=tp_input,
-                          perturb_u=None if pu is None else pu[:, i:i + chunk], **kwargs)
+                          perturb_u=None if pu is None else pu[:, i:i + chunk],
+                          smooth_delta=None if sd is None else sd[:, i * S:(i + chunk) * S], **kwargs)
+        if "_normal_fields" in ret:
+            raise NotImplementedError("a smooth-loss step goes through render() in one pass (training batches are a few "
+                                      "thousand rays); chunked ray sets are an inference feature")
         for k, v in ret.items():
             all_ret.setdefault(k, []).append(v)
     return {k: torch.cat(v, 1) for k, v in all_ret.items()}
@@ -237,7 +249,7 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
         if not torch.cuda.is_available():
             raise RuntimeError("mpsnerf_b200 has no CPU path: a CUDA device is required")
         dev = torch.device("cuda", torch.cuda.current_device())
-        sp_input, tp_input = _upload_hot(sp_input, HOT_KEYS_SP, dev), _upload_hot(tp_input, HOT_KEYS_TP, dev)
+        sp_input, tp_input = _upload_hot(sp_input, HOT_KEYS_SP + STEP_KEYS, dev), _upload_hot(tp_input, HOT_KEYS_TP, dev)
     box = None
     if rays is None:
         if camera is None:
@@ -281,7 +293,15 @@ def render(H=None, W=None, focal=None, chunk=1024 * 32, rays=None, c2w=None, ndc
     else:
         ret = render_rays(packed, sp_input=sp_input, tp_input=tp_input, _rays_ready=ready, **kwargs)
     nchunks = max(1, (n + chunk - 1) // chunk)
-    ret["other_loss"] = torch.zeros(1, 4 * nchunks, device=packed.device)
+    fields = ret.pop("_normal_fields", None)
+    if fields is None:
+        ret["other_loss"] = torch.zeros(1, 4 * nchunks, device=packed.device)
+    else:
+        # smooth step: the reference evaluates the two terms once per ray chunk (means over that chunk's sample points)
+        # and concatenates the (1,4) blocks, ref :62-78 + :85-97; the training loop reads block 0
+        from .smooth import smooth_losses
+        cut = lambda t, i: t[:, i * chunk * S_:(i + 1) * chunk * S_]
+        ret["other_loss"] = torch.cat([smooth_losses(*(cut(t, i) for t in fields)) for i in range(nchunks)], 1)
     for k in ("rgb_map", "disp_map", "acc_map", "pts_mask", "raw"):
         ret[k] = torch.reshape(ret[k], list(sh[:-1]) + list(ret[k].shape[2:]))
     if box is not None:

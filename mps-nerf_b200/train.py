@@ -7,8 +7,11 @@ runs hand-written backward kernels: K6 backward, the dense backward (weight grad
 MLP, token gradients) and K4 backward (scatter-add into the NHWC latent gradient), after which torch / cuDNN
 backpropagates through the encoder trunk -- the boundary of the path, as in the forward.  Under the shipped configs
 no parameter sits upstream of the canonical points (skinning_field = correction_field = 0), so K1 / K3 need no
-backward; the smooth-loss second pass (normals by double backward, every ``smooth_interval``-th step) is not built
-and raises.
+backward.  Every ``smooth_interval``-th step adds the normal-smoothness terms (occupancy normals by double backward at
+the sample points and at perturbed copies of them, ref run_nerf_batch.py:60-79): K1 / K3 locate both point sets
+(mask, canonical points, nearest template vertices), the twice-differentiable chain on the active points is the
+torch-autograd restatement of smooth.py, and its parameter gradients join the kernels' in the same bucket before the
+all-reduce.
 
 Data parallelism (``TrainStep``): one process per GPU, replicas of the network, ONE NCCL all-reduce of the
 dense-stage gradients (46 tensors, 1.08 M floats, kept in one flat bucket the backward kernels accumulate into
@@ -46,15 +49,26 @@ class DenseBucket:
         self.pending = 0            # autograd nodes of this step that have not run their backward yet
         self.work = None            # handle of the in-flight all-reduce
         self.world = 1
+        self.deferred = False       # smooth step: autograd also writes p.grad; the all-reduce waits for absorb_autograd()
 
     def begin_step(self, world):
         self.flat.zero_()
-        self.pending, self.work, self.world = 0, None, world
+        self.pending, self.work, self.world, self.deferred = 0, None, world, False
 
     def node_done(self):
         """Called at the end of every render node's backward; the last one launches the all-reduce."""
         self.pending -= 1
-        if self.pending == 0 and self.world > 1:
+        if self.pending == 0 and self.world > 1 and not self.deferred:
+            self.work = dist.all_reduce(self.flat, async_op=True)
+
+    def absorb_autograd(self):
+        """Smooth step: the torch-autograd chain of smooth.py accumulated its share of the dense-stage gradients in
+        ``p.grad``; add them to the kernels' share in the flat buffer, then launch the all-reduce that was held back."""
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.add_(p.grad)
+                p.grad = None
+        if self.deferred and self.world > 1 and self.work is None:
             self.work = dist.all_reduce(self.flat, async_op=True)
 
     def finish(self):
@@ -72,7 +86,7 @@ class _RenderNode(torch.autograd.Function):
     """One subject's render: latent (V, Hf, Wf, 128) -> rgb_map, acc_map (+ the non-differentiable extras)."""
 
     @staticmethod
-    def forward(ctx, latent, te, fctx, img4, rays8, S, t_vals, u, occupancy):
+    def forward(ctx, latent, te, fctx, img4, rays8, S, t_vals, u, occupancy, located):
         eng, lib, dev = te.eng, te.eng.lib, latent.device
         N = rays8.shape[0]
         P, V = N * S, fctx.n_views
@@ -95,11 +109,12 @@ class _RenderNode(torch.autograd.Function):
         tokens = torch.empty(max(n, 1), V, _lib.TOKEN_DIM, device=dev)
         out4 = torch.empty(max(n, 1), 4, device=dev)
         ws = torch.empty(max(lib.mpsnerf_dense_train_workspace(n, V), 256), dtype=torch.uint8, device=dev)
+        idx3 = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if located is not None else None
         if n:
             fctx.wait_lbs()
             _lib.check(lib.mpsnerf_deform_project(_lib.ptr(act_pid), _lib.ptr(act_idx2), _lib.ptr(act_q), 0, n, _lib.ptr(fctx.skin_w),
                                                   _lib.ptr(fctx.frame_dev), _lib.ptr(fctx.grid_tv), _lib.ptr(xc), _lib.ptr(uv),
-                                                  _lib.ptr(ss), None, None, 0, _stream()), "deform_project")
+                                                  _lib.ptr(ss), _lib.ptr(idx3), None, 0, _stream()), "deform_project")
             _lib.check(lib.mpsnerf_gather_tokens(_lib.ptr(uv), n, V, _lib.ptr(fctx.frame_dev), _lib.ptr(latent), _lib.ptr(img4),
                                                  _lib.ptr(tokens), _lib.TOKEN_DIM, _stream()), "gather_tokens")
             _lib.check(lib.mpsnerf_dense_train_fwd(_lib.ptr(tokens), _lib.TOKEN_DIM, _lib.ptr(xc), n, V, te.bucket.wtable,
@@ -112,6 +127,8 @@ class _RenderNode(torch.autograd.Function):
                                          1 if occupancy else 0, _lib.ptr(rgb), _lib.ptr(disp), _lib.ptr(acc), None, None, None,
                                          _stream()), "composite")
         _lib.count_launches(6 + 44)
+        if located is not None:     # smooth step: the index stages of this pass, for smooth.normal_fields
+            located.update(act_pid=act_pid, xc=xc[:n], idx3=idx3[:n])
         eng.last_active = n
         ctx.te, ctx.fctx, ctx.n, ctx.S, ctx.occupancy = te, fctx, n, S, occupancy
         ctx.keep = (rays8, t_vals, u, raw, act_pid, uv, ws, latent.shape)
@@ -143,7 +160,7 @@ class _RenderNode(torch.autograd.Function):
                                                      _lib.TOKEN_DIM, _lib.ptr(d_latent), _stream()), "gather_tokens_bwd")
             _lib.count_launches(3 + 80)
         te.bucket.node_done()
-        return (d_latent,) + (None,) * 8
+        return (d_latent,) + (None,) * 9
 
 
 class TrainEngine:
@@ -155,20 +172,73 @@ class TrainEngine:
         self.eng = RenderEngine(net, precision="fp32")
         self.bucket = DenseBucket(net)
 
-    def render_subject(self, sp, tp, rays8, S, t_vals, u, occupancy):
-        """sp / tp: one subject's (squeezed) dicts on the device.  -> rgb (N,3), acc (N), disp, raw, mask, sq, ss."""
+    def render_subject(self, sp, tp, rays8, S, t_vals, u, occupancy, smooth_pts=None):
+        """sp / tp: one subject's (squeezed) dicts on the device.  -> rgb (N,3), acc (N), disp, raw, mask, sq, ss and,
+        on a smooth step (``smooth_pts`` = the perturbed sample points (N*S,3)), the three normal fields
+        (occ0, smpl0, occ1), each (N*S,3); None otherwise."""
         net = self.net
         net._check_supported()
         fctx = self.eng.prepare_frame(sp, tp, net._smpl_for(sp["gender"]), trunk=False)
         img = sp["img_all"].to(tp["vertices"].device, non_blocking=True).float()
-        latent = net.encoder_2d(img)                               # torch / cuDNN under autograd: the path's boundary
-        latent = latent.permute(0, 2, 3, 1).contiguous().float()
+        latent_nchw = net.encoder_2d(img)                          # torch / cuDNN under autograd: the path's boundary
+        latent = latent_nchw.permute(0, 2, 3, 1).contiguous().float()
         img4 = F.pad(img.permute(0, 2, 3, 1), (0, 1)).contiguous()
-        return _RenderNode.apply(latent, self, fctx, img4, rays8, S, t_vals, u, occupancy)
+        located = {} if smooth_pts is not None else None
+        out = _RenderNode.apply(latent, self, fctx, img4, rays8, S, t_vals, u, occupancy, located)
+        if smooth_pts is None:
+            return out, None
+        from . import smooth
+        P = rays8.shape[0] * S
+        # (copies: the frame buffer belongs to the engine and is rewritten by the next subject's preparation, while
+        # autograd keeps these constants for the backward)
+        fctx.wait_lbs()
+        fr = {k: v.clone() for k, v in smooth.frame_constants(fctx.frame_dev, fctx.n_views).items()}
+        normals = smooth.vertex_normals(sp["t_vertices"].float(), net.faces.to(img.device))
+        occ0, smpl0 = smooth.normal_fields(net, fr, latent_nchw, img, fctx.skin_w, normals, P, located["act_pid"],
+                                           located["xc"], located["idx3"])
+        second = self.locate(fctx, smooth_pts)
+        occ1, _ = smooth.normal_fields(net, fr, latent_nchw, img, fctx.skin_w, normals, P, second["act_pid"],
+                                       second["xc"], second["idx3"])
+        return out, (occ0, smpl0, occ1)
+
+    def locate(self, fctx, points):
+        """The index stages of a network pass on explicit world points (the perturbed pass of a smooth step): K1 in
+        its points mode (mask, nearest posed vertex, compaction) and K3 (canonical point, nearest template vertex).
+        -> dict(act_pid (n) int32, xc (n,3), idx3 (n) int32)."""
+        lib, dev = self.eng.lib, points.device
+        points = points.float().contiguous()
+        P, V = points.shape[0], fctx.n_views
+        raw = torch.empty(P, 4, device=dev)
+        mask = torch.empty(P, device=dev)
+        sq = torch.empty(P, 3, device=dev)
+        ss = torch.empty(P, 3, device=dev)
+        act_pid = torch.empty(P, dtype=torch.int32, device=dev)
+        act_idx2 = torch.empty(P, dtype=torch.int32, device=dev)
+        act_q = torch.empty(P, 3, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.mpsnerf_sample_knn(None, P, 1, None, None, _lib.ptr(points), _lib.ptr(fctx.frame_dev),
+                                          _lib.ptr(fctx.grid_tp), _lib.ptr(raw), _lib.ptr(mask), _lib.ptr(sq), _lib.ptr(ss),
+                                          _lib.ptr(act_pid), _lib.ptr(act_idx2), _lib.ptr(act_q), _lib.ptr(counter), _stream()),
+                   "sample_knn")
+        n = int(counter.item())
+        act_pid = act_pid[:n].clone()
+        xc = torch.empty(max(n, 1), 3, device=dev)
+        uv = torch.empty(max(n, 1), V, 2, device=dev)
+        idx3 = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        if n:
+            fctx.wait_lbs()
+            _lib.check(lib.mpsnerf_deform_project(_lib.ptr(act_pid), _lib.ptr(act_idx2), _lib.ptr(act_q), 0, n, _lib.ptr(fctx.skin_w),
+                                                  _lib.ptr(fctx.frame_dev), _lib.ptr(fctx.grid_tv), _lib.ptr(xc), _lib.ptr(uv),
+                                                  _lib.ptr(ss), _lib.ptr(idx3), None, 0, _stream()), "deform_project")
+        _lib.count_launches(2)
+        return {"act_pid": act_pid, "xc": xc[:n], "idx3": idx3[:n]}
 
 
-def render_rays_train(net, ray_batch, sp_input, tp_input, N_samples, perturb, perturb_u, white_bkgd, occupancy, select):
-    """Training-mode body of run_nerf_batch.render_rays: same dict of outputs, rgb_map / acc_map carry gradients."""
+def render_rays_train(net, ray_batch, sp_input, tp_input, N_samples, perturb, perturb_u, white_bkgd, occupancy, select,
+                      smooth_step=False, smooth_delta=None):
+    """Training-mode body of run_nerf_batch.render_rays: same dict of outputs, rgb_map / acc_map carry gradients.
+    ``smooth_step``: also evaluate the normal-smoothness terms into ``other_loss`` (ref run_nerf_batch.py:60-79);
+    ``smooth_delta`` (B, C*S, 3) supplies the perturbation of the second pass (N(0, 0.01) otherwise, :36, :64)."""
     te = net.train_engine()
     B, C = ray_batch.shape[:2]
     dev = ray_batch.device
@@ -177,19 +247,32 @@ def render_rays_train(net, ray_batch, sp_input, tp_input, N_samples, perturb, pe
     u = None
     if perturb > 0.0:
         u = (perturb_u if perturb_u is not None else torch.rand(B, C, S, device=dev)).float().contiguous()
-    per = []
+    pts1 = None
+    if smooth_step:
+        from . import smooth
+        te.bucket.deferred = True           # autograd will add to p.grad: TrainStep merges before the all-reduce
+        delta = smooth_delta.to(dev).float() if smooth_delta is not None else 0.01 * torch.randn(B, C * S, 3, device=dev)
+        pts1 = smooth.sample_points(ray_batch[..., :8].float(), t_vals, u).reshape(B, C * S, 3) + delta.reshape(B, C * S, 3)
+    per, fields = [], []
     for b in range(B):
         sp, tp = select(sp_input, b), select(tp_input, b)
-        per.append(te.render_subject(sp, tp, ray_batch[b, :, :8].float().contiguous(), S, t_vals,
-                                     None if u is None else u[b].contiguous(), occupancy))
+        out, nf = te.render_subject(sp, tp, ray_batch[b, :, :8].float().contiguous(), S, t_vals,
+                                    None if u is None else u[b].contiguous(), occupancy,
+                                    smooth_pts=None if pts1 is None else pts1[b])
+        per.append(out)
+        fields.append(nf)
     st = lambda i, *shape: torch.stack([r[i].reshape(C, *shape) for r in per], 0)
     rgb, acc = st(0, 3), st(1)
     if white_bkgd:
         rgb = rgb + (1.0 - acc[..., None])
-    zeros3 = torch.zeros(1, 1, 1, 1, device=dev).expand(B, C, S, 3)
-    return {"rgb_map": rgb, "disp_map": st(2), "acc_map": acc, "smpl_query_pts": st(5, S, 3), "smpl_src_pts": st(6, S, 3),
-            "correction_": zeros3, "other_loss": torch.zeros(1, 4, device=dev), "correction": zeros3,
-            "pts_mask": st(4, S, 1), "raw": st(3, S, 4)}
+    out = {"rgb_map": rgb, "disp_map": st(2), "acc_map": acc, "smpl_query_pts": st(5, S, 3), "smpl_src_pts": st(6, S, 3),
+           "other_loss": torch.zeros(1, 4, device=dev), "pts_mask": st(4, S, 1), "raw": st(3, S, 4)}
+    out["correction"] = out["correction_"] = torch.zeros(1, 1, 1, 1, device=dev).expand(B, C, S, 3)
+    if smooth_step:
+        occ0, smpl0, occ1 = (torch.stack([f[i] for f in fields], 0) for i in range(3))      # (B, C*S, 3) each
+        out["other_loss"] = smooth.smooth_losses(occ0, smpl0, occ1)
+        out["_normal_fields"] = (occ0, smpl0, occ1)      # render() re-cuts the terms per ray chunk, as the reference does
+    return out
 
 
 def img2mse(x, y):
@@ -220,7 +303,9 @@ class TrainStep:
         loss = img2mse(rgb, target_rgb)
         if self.acc_loss and bkgd_msk is not None:
             loss = loss + img2mse(bkgd_msk.squeeze(2), acc)
+        loss = loss + extras["other_loss"][0][0]          # the smooth terms on interval steps, 0 otherwise (:558)
         loss.backward()
+        bucket.absorb_autograd()
         self.allreduce_trunk(world)
         bucket.finish()
         self.optimizer.step()

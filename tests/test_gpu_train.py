@@ -189,3 +189,58 @@ def test_train_step_optimises():
     with torch.no_grad():
         out = R.render(network_fn=handle, **dict(kw, perturb=False, perturb_u=None))
     assert not out[0].requires_grad and torch.isfinite(out[0]).all()
+
+
+def test_smooth_step_against_reference_double_backward(strict_fp32_convs):
+    """An interval step of the shipped configs (smooth_loss = 1, global_step % smooth_interval == 0): render() in
+    training mode returns the two normal-smoothness terms in extras['other_loss'] and their gradients -- K1 / K3
+    locate the sample points and their perturbed copies, smooth.py differentiates the active points twice -- against
+    the UNMODIFIED reference's own double backward (tests/golden/smooth_grads.npz, oracle/make_golden_smooth.py).
+    Tolerances: see tests/test_smooth_cpu.py (the terms are functions of normalised gradients)."""
+    from test_smooth_cpu import GOLD, check_smooth_grads, smooth_keys
+    from mpsnerf_b200.parser_config import config_parser
+    g = np.load(GOLD)
+    R, net, handle, kw, target, msk = _train_setup()
+    R.configure(config_parser().parse_args(["--smooth_loss", "1"]))
+    sp = dict(kw["sp_input"])
+    sp["global_step"] = torch.zeros(1, dtype=torch.long)
+    sp["smooth_interval"] = torch.full((1,), 4, dtype=torch.long)
+    kw = dict(kw, sp_input=sp, smooth_delta=torch.from_numpy(g["delta"])[None].cuda())
+    bucket = net.train_engine().bucket
+    bucket.begin_step(1)
+    rgb, disp, acc, extras = R.render(network_fn=handle, **kw)
+    other = extras["other_loss"]
+    assert other.shape == (1, 4) and other.requires_grad
+    np.testing.assert_allclose(other.detach().cpu().numpy().reshape(4), g["other_loss"], rtol=5e-4, atol=1e-7)
+    other[0][0].backward()
+    bucket.absorb_autograd()
+    bucket.finish()
+    named = dict(net.named_parameters())
+    grads = {k: named[k].grad for k in smooth_keys()}
+    assert all(v is not None for v in grads.values())
+    check_smooth_grads(grads, g, rtol_norm=2e-2, rtol_val=0.15, min_cos=0.995)
+    # a step that is not on the interval carries no smooth terms
+    sp["global_step"] = torch.ones(1, dtype=torch.long)
+    bucket.begin_step(1)
+    extras = R.render(network_fn=handle, **kw)[3]
+    assert not extras["other_loss"].requires_grad and float(extras["other_loss"].abs().sum()) == 0.0
+
+
+def test_train_step_with_smooth_terms_optimises():
+    """TrainStep over four consecutive global steps with the shipped smooth_loss = 1: step 0 takes the smooth path,
+    steps 1..3 the plain one; the loss stays finite and the parameters move."""
+    from mpsnerf_b200.train import TrainStep
+    from mpsnerf_b200.parser_config import config_parser
+    R, net, handle, kw, target, msk = _train_setup()
+    R.configure(config_parser().parse_args(["--smooth_loss", "1"]))
+    opt = torch.optim.Adam([p for p in net.parameters()], lr=2e-5, betas=(0.9, 0.999))
+    ts = TrainStep(handle, opt, acc_loss=True)
+    w0 = net.alpha_linear.weight.detach().clone()
+    losses = []
+    for step in range(4):
+        sp = dict(kw["sp_input"])
+        sp["global_step"] = torch.full((1,), step, dtype=torch.long)
+        sp["smooth_interval"] = torch.full((1,), 4, dtype=torch.long)
+        losses.append(float(ts.step(R.render, target_rgb=target, bkgd_msk=msk, **dict(kw, sp_input=sp))))
+    assert all(np.isfinite(losses)), losses
+    assert not torch.equal(w0, net.alpha_linear.weight.detach())
