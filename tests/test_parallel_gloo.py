@@ -138,6 +138,24 @@ def _bucket_worker(rank, world, port, out):
     want = sum(11.0 * (r + 1) for r in range(world)) / world
     for p in b.params:
         assert p.grad is not None and torch.allclose(p.grad, torch.full_like(p, want))
+    # smooth step: autograd adds its share to p.grad, the all-reduce is held back until both shares are merged
+    for p in b.params:
+        p.grad = None
+    b.begin_step(world)
+    b.deferred = True
+    b.pending = 1
+    for v in b.views:
+        v += float(rank + 1)               # the kernels' share
+    b.node_done()
+    assert b.work is None                  # held back
+    for p in b.params:
+        p.grad = torch.full_like(p, 100.0 * (rank + 1))      # the torch-autograd share (smooth.py)
+    b.absorb_autograd()
+    assert b.work is not None and all(p.grad is None for p in b.params)
+    b.finish()
+    want = sum(101.0 * (r + 1) for r in range(world)) / world
+    for p in b.params:
+        assert torch.allclose(p.grad, torch.full_like(p, want))
     # trunk gradients: one flat all-reduce, averaged
     ts = TrainStep(net, optimizer=None)
     for p in net.encoder_2d.parameters():
