@@ -76,7 +76,8 @@ def run_network(inputs, viewdirs, fn, sp_input=None, tp_input=None):
     out = torch.reshape(out, list(inputs.shape[:-1]) + [out.shape[-1]])
     net = _net_of(fn)
     if net.training and global_args.smooth_loss and torch.is_grad_enabled():
-        raise NotImplementedError("smooth-loss second pass needs the (unbuilt) double-backward path")
+        raise NotImplementedError("the smooth-loss second pass runs inside render() (mps-nerf_b200/train.py + smooth.py: it "
+                                  "needs the active-point lists of both passes); run_network() itself is forward only")
     return out, torch.zeros(1, 4, device=inputs.device)
 
 

@@ -43,12 +43,23 @@ def frame_constants(frame_dev, n_views):
             "cam_K": get("cam_K").view(-1, 3, 3)[:n_views]}
 
 
+def inverse3(A):
+    """(n,3,3) -> inverses by the adjugate (the formula K3 uses, csrc/deform.cu): elementwise ops only, so no
+    cuSOLVER call (and none of its host synchronisations) and a cheap double backward."""
+    a, b, c, d, e, f, g, h, i = (A[:, r, k] for r in range(3) for k in range(3))
+    c00, c01, c02 = e * i - f * h, c * h - b * i, b * f - c * e
+    c10, c11, c12 = f * g - d * i, a * i - c * g, c * d - a * f
+    c20, c21, c22 = d * h - e * g, b * g - a * h, a * e - b * d
+    det = a * c00 + b * c10 + c * c20
+    return torch.stack([c00, c01, c02, c10, c11, c12, c20, c21, c22], -1).view(-1, 3, 3) / det[:, None, None]
+
+
 def canonical_to_pixels(xc, bw, fr):
     """x_c (n,3) -> pixel coordinates (V,n,2) in the input views: coarse_deform_c2source (:253-300, nearest vertex
     frozen: ``bw`` = its normalised blend weights (n,24)) and projection (:177-184).  fr: frame_constants()."""
     A = (bw @ fr["A_big_sp"]).view(-1, 3, 4)                      # big pose -> T pose, inverted
     q = xc - A[:, :, 3]
-    q = (torch.inverse(A[:, :, :3]) * q[:, None]).sum(2)
+    q = (inverse3(A[:, :, :3]) * q[:, None]).sum(2)
     A = (bw @ fr["A_sp"]).view(-1, 3, 4)                          # T pose -> source pose
     s = (A[:, :, :3] * q[:, None]).sum(2) + A[:, :, 3]
     w = s @ fr["Rinv_sp"] + fr["Th_sp"]                           # SMPL space -> world (:297-298)
