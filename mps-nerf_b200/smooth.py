@@ -120,20 +120,25 @@ def occupancy_normals(net, fr, latent, img, xc, bw):
     return g / (torch.norm(g, dim=-1, keepdim=True) + 1e-8)
 
 
-def normal_fields(net, fr, latent, img, skin_w, vertex_normals, n_points, act_pid, xc, idx3):
-    """The two (P,3) fields the network output carries in columns 17:23 on a smooth step (:484-503): the occupancy
-    normal and the normal of the nearest template vertex, zero outside the human region."""
-    dev = xc.device
-    occ_all = torch.zeros(n_points, 3, device=dev, dtype=xc.dtype)
-    smpl_all = torch.zeros(n_points, 3, device=dev, dtype=xc.dtype)
-    if act_pid.numel() == 0:
-        return occ_all, smpl_all
-    bw = skin_w[idx3.long()]
+def normal_fields(net, fr, latent, img, skin_w, vertex_normals, n_points, first, second):
+    """The fields the network output carries in columns 17:23 on a smooth step (:484-503), for the two passes of
+    run_nerf_batch.py:62-67 at once: ``first`` / ``second`` = dict(act_pid (n), xc (n,3), idx3 (n)) of the unperturbed
+    and of the perturbed sample points.  -> (occ0, smpl0, occ1), each (n_points,3): occupancy normal of pass 0, normal
+    of the nearest template vertex of pass 0, occupancy normal of pass 1; zero outside the human region.  The active
+    points of both passes go through the chain as ONE batch (every stage is per point), which halves its launches."""
+    dev, dt = first["xc"].device, first["xc"].dtype
+    n0 = first["act_pid"].numel()
+    xc = torch.cat((first["xc"], second["xc"]), 0)
+    idx3 = torch.cat((first["idx3"], second["idx3"]), 0).long()
+    zeros = lambda: torch.zeros(n_points, 3, device=dev, dtype=dt)
+    if xc.shape[0] == 0:
+        return zeros(), zeros(), zeros()
+    bw = skin_w[idx3]
     bw = bw / bw.sum(-1, keepdim=True)                                               # :261-262
-    pid = act_pid.long()
-    occ_all = occ_all.index_put((pid,), occupancy_normals(net, fr, latent, img, xc, bw))
-    smpl_all = smpl_all.index_put((pid,), vertex_normals[idx3.long()])
-    return occ_all, smpl_all
+    occ = occupancy_normals(net, fr, latent, img, xc, bw)
+    pid0, pid1 = first["act_pid"].long(), second["act_pid"].long()
+    return (zeros().index_put((pid0,), occ[:n0]), zeros().index_put((pid0,), vertex_normals[idx3[:n0]]),
+            zeros().index_put((pid1,), occ[n0:]))
 
 
 def smooth_losses(occ0, smpl0, occ1):

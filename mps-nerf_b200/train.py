@@ -194,11 +194,8 @@ class TrainEngine:
         fctx.wait_lbs()
         fr = {k: v.clone() for k, v in smooth.frame_constants(fctx.frame_dev, fctx.n_views).items()}
         normals = smooth.vertex_normals(sp["t_vertices"].float(), net.faces.to(img.device))
-        occ0, smpl0 = smooth.normal_fields(net, fr, latent_nchw, img, fctx.skin_w, normals, P, located["act_pid"],
-                                           located["xc"], located["idx3"])
         second = self.locate(fctx, smooth_pts)
-        occ1, _ = smooth.normal_fields(net, fr, latent_nchw, img, fctx.skin_w, normals, P, second["act_pid"],
-                                       second["xc"], second["idx3"])
+        occ0, smpl0, occ1 = smooth.normal_fields(net, fr, latent_nchw, img, fctx.skin_w, normals, P, located, second)
         return out, (occ0, smpl0, occ1)
 
     def locate(self, fctx, points):

@@ -73,19 +73,19 @@ def test_smooth_terms_and_gradients_match_reference_double_backward():
     latent = net.encoder_2d(img)
     skin_w = torch.from_numpy(c["W"])
     normals = smooth.vertex_normals(sp["t_vertices"].float(), net.faces)
-    fields, counts = [], []
+    locs = []
     for p in (pts.numpy(), pts.numpy() + g["delta"]):
         act, xc, idx3 = _locate(p, c)
-        counts.append(len(act))
-        fields.append(smooth.normal_fields(net, fr, latent, img, skin_w, normals, P, act, xc, idx3))
-    assert counts[0] == int(g["n_active"])
+        locs.append({"act_pid": act, "xc": xc, "idx3": idx3})
+    occ0, smpl0, occ1 = smooth.normal_fields(net, fr, latent, img, skin_w, normals, P, locs[0], locs[1])
+    assert locs[0]["act_pid"].numel() == int(g["n_active"])
     # (points whose alpha gradient is exactly zero -- every path through a dead ReLU -- get a zero normal, in both)
-    assert int((fields[0][0].abs().sum(-1) > 0).sum()) == int((np.abs(g["occ_normal"]).sum(-1) > 0).sum())
-    other = smooth.smooth_losses(fields[0][0], fields[0][1], fields[1][0])
+    assert int((occ0.abs().sum(-1) > 0).sum()) == int((np.abs(g["occ_normal"]).sum(-1) > 0).sum())
+    other = smooth.smooth_losses(occ0, smpl0, occ1)
     # the field itself: unit normals, so absolute tolerance; a point whose gradient is tiny amplifies rounding
-    np.testing.assert_allclose(fields[0][1].detach().numpy(), g["smpl_normal"], atol=1e-6)
+    np.testing.assert_allclose(smpl0.detach().numpy(), g["smpl_normal"], atol=1e-6)
     live = np.abs(g["occ_normal"]).sum(-1) > 0
-    d = np.abs(fields[0][0].detach().numpy() - g["occ_normal"]).max(-1)[live]
+    d = np.abs(occ0.detach().numpy() - g["occ_normal"]).max(-1)[live]
     # (a normalised gradient: the few points whose raw gradient is ~1e-6 long amplify fp32 rounding to ~0.1)
     assert np.quantile(d, 0.98) < 1e-3 and (d > 1e-2).sum() <= 4, (np.quantile(d, 0.98), np.sort(d)[-6:])
     np.testing.assert_allclose(other.detach().numpy().reshape(4), g["other_loss"], rtol=2e-4, atol=1e-7)
