@@ -33,6 +33,7 @@ extern "C" {
 #define MPSNERF_EINVAL (-1)   /* bad argument (null pointer, size out of range) */
 #define MPSNERF_ECUDA (-2)    /* a CUDA runtime call or launch failed */
 #define MPSNERF_EARCH (-3)    /* device is not sm_100 */
+#define MPSNERF_ENCCL (-4)    /* libnccl could not be bound, or ncclAllReduce returned an error */
 
 #define MPSNERF_MAX_VIEWS 8
 #define MPSNERF_NUM_JOINTS 24
@@ -218,6 +219,15 @@ int mpsnerf_gather_tokens_bwd(const float* uv, int64_t count, int n_views, const
                               const float* d_tokens, int32_t ld, float* d_latent, void* stream);
 int mpsnerf_rows4_gather(const float* src, const int32_t* act_pid, int64_t count, float* dst, void* stream);
 int mpsnerf_rows4_scatter(const float* src, const int32_t* act_pid, int64_t count, float* dst, void* stream);
+
+/* The gradient all-reduce of data-parallel training -- the one collective of the path.  Replaces what
+ * DistributedDataParallel does behind loss.backward() (run_nerf_batch.py:344-348, :560): `bucket` (count floats, e.g. the
+ * flat buffer the dense backward accumulated the 46 gradients into) is averaged IN PLACE over the ranks of `nccl_comm`
+ * (an ncclComm_t owned by the host, passed as void*), enqueued on `stream` behind the backward kernels: one
+ * ncclAllReduce with ncclAvg.  The library does not link NCCL: the symbol is bound at first use from the libnccl already
+ * loaded in the process (else libnccl.so.2 from the loader path); MPSNERF_ENCCL if that fails or NCCL reports an error.
+ * The Python mirror (mps-nerf_b200/train.py) uses torch.distributed's communicator instead and does not call this. */
+int mpsnerf_allreduce_mean(void* nccl_comm, float* bucket, int64_t count, void* stream);
 
 /* bf16 tensor-core variant (tcgen05 / TMEM / bulk-async weight streaming).  `packed` is the
  * blob produced by mpsnerf_b200.engine.pack_weights_bf16 (layout: DESIGN.md section 5). */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "mpsnerf_gather_tokens_bwd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "mpsnerf_rows4_gather": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "mpsnerf_rows4_scatter": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mpsnerf_allreduce_mean": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "mpsnerf_dense_bf16_workspace": (c_size_t, [c_int64, c_int]),
     "mpsnerf_dense_bf16": (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p,
                                    c_int64, c_void_p, c_void_p, c_void_p]),

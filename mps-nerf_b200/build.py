@@ -85,7 +85,7 @@ def _build_locked(force, verbose, objdir):
     if failed:
         raise RuntimeError("nvcc failed")
     tmp = LIB + ".tmp.%d" % os.getpid()
-    subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-lcudart", "-ldl"])
     os.replace(tmp, LIB)
     with open(HASH_FILE + ".tmp", "w") as fh:
         fh.write(source_hash())

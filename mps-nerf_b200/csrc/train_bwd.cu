@@ -171,3 +171,47 @@ extern "C" int mpsnerf_rows4_scatter(const float* src, const int32_t* act_pid, i
   MPS_LAUNCH_CHECK();
   return MPSNERF_OK;
 }
+
+// ------------------------------------------------------------------ the gradient all-reduce of data-parallel training
+// The one collective of the path (run_nerf_batch.py:344-348: DistributedDataParallel around the network).  The
+// communicator belongs to the host (a C / C++ trainer creates it with ncclCommInitRank; the Python mirror uses
+// torch.distributed instead and never calls this).  The library does not link NCCL: ncclAllReduce is bound at first
+// use from the libnccl the process has already loaded, else from libnccl.so.2 on the loader path.
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace mps {
+using AllReduceFn = ncclResult_t (*)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+using ErrStrFn = const char* (*)(ncclResult_t);
+static AllReduceFn g_allreduce = nullptr;
+static ErrStrFn g_errstr = nullptr;
+
+static bool bind_nccl() {
+  if (g_allreduce) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return false;
+  g_errstr = reinterpret_cast<ErrStrFn>(dlsym(h, "ncclGetErrorString"));
+  g_allreduce = reinterpret_cast<AllReduceFn>(dlsym(h, "ncclAllReduce"));
+  return g_allreduce != nullptr;
+}
+}  // namespace mps
+
+extern "C" int mpsnerf_allreduce_mean(void* nccl_comm, float* bucket, int64_t count, void* stream) {
+  MPS_REQUIRE(count >= 0);
+  if (count == 0) return MPSNERF_OK;
+  MPS_REQUIRE(nccl_comm && bucket);
+  if (!mps::bind_nccl()) {
+    mps::set_error("%s", "mpsnerf_allreduce_mean: libnccl.so.2 not found (dlopen)");
+    return MPSNERF_ENCCL;
+  }
+  // in place, averaged by the collective itself (ncclAvg: with NVLS the sum and the scale happen in the switch)
+  const ncclResult_t r = mps::g_allreduce(bucket, bucket, (size_t)count, ncclFloat32, ncclAvg,
+                                          static_cast<ncclComm_t>(nccl_comm), (cudaStream_t)stream);
+  if (r != ncclSuccess) {
+    mps::set_error("mpsnerf_allreduce_mean: ncclAllReduce: %s", mps::g_errstr ? mps::g_errstr(r) : "failed");
+    return MPSNERF_ENCCL;
+  }
+  return MPSNERF_OK;
+}
