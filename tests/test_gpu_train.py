@@ -244,3 +244,65 @@ def test_train_step_with_smooth_terms_optimises():
         losses.append(float(ts.step(R.render, target_rgb=target, bkgd_msk=msk, **dict(kw, sp_input=sp))))
     assert all(np.isfinite(losses)), losses
     assert not torch.equal(w0, net.alpha_linear.weight.detach())
+
+
+def test_smooth_step_batch_of_two_equals_the_per_subject_steps(strict_fp32_convs):
+    """B = 2 subjects (male / female tables, different poses and rays) in one smooth step: the terms are means over
+    both subjects' sample points (the reference evaluates them on the gathered DataParallel output, ref :60-79), so
+    other_loss and its gradients must equal the average of the two B = 1 steps -- which
+    test_smooth_step_against_reference_double_backward pins to the reference."""
+    from conftest import load_batch_case
+    from test_smooth_cpu import smooth_keys
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    from mpsnerf_b200.lib import skinnning_batch as SB
+    from mpsnerf_b200.parser_config import config_parser
+    scenes, sd, sp, tp, models, g = load_batch_case("batch2")
+    SB.set_default_smpl_models(models)
+    torch.manual_seed(0)
+    net = SB.SKinningBatch(human_sample=1, use_f2d=1, use_trans=1, smooth_loss=1, num_instances=25, mean_shape=0,
+                           correction_field=0, skinning_field=0, data_set_type="THuman_B", append_rgb=1, with_viewdirs=0,
+                           precision="fp32")
+    net.load_state_dict(sd, strict=False)
+    net = net.cuda().train()
+    R.configure(config_parser().parse_args(["--smooth_loss", "1"]))
+    handle = R.NetworkHandle(net)
+    S = int(g["S"])
+    parts = [synthetic.rays_tensor(sc, g["ray_ids"][b], device="cuda") for b, sc in enumerate(scenes)]
+    rays, near, far = (torch.cat([p[k] for p in parts], 0) for k in range(3))
+    n = rays.shape[2]
+    gen = torch.Generator().manual_seed(11)
+    delta = (0.01 * torch.randn(2, n * S, 3, generator=gen)).cuda()
+    u = torch.rand(2, n, S, generator=gen).cuda()
+    step = dict(global_step=torch.zeros(2, dtype=torch.long), smooth_interval=torch.full((2,), 4, dtype=torch.long))
+    sp_d, tp_d = dict(_cuda_dict(sp), **step), _cuda_dict(tp)
+    cut = lambda d, b: {k: (cut(v, b) if isinstance(v, dict) else v[b:b + 1]) for k, v in d.items()}
+    keys = smooth_keys()
+    named = dict(net.named_parameters())
+    bucket = net.train_engine().bucket
+
+    def run(sp_in, tp_in, sl):
+        for p in net.parameters():
+            p.grad = None
+        bucket.begin_step(1)
+        extras = R.render(rays=rays[sl], near=near[sl], far=far[sl], sp_input=sp_in, tp_input=tp_in, network_fn=handle,
+                          N_samples=S, perturb=1.0, perturb_u=u[sl], smooth_delta=delta[sl], use_viewdirs=True)[3]
+        other = extras["other_loss"]
+        other[0][0].backward()
+        bucket.absorb_autograd()
+        bucket.finish()
+        return other.detach().clone(), {k: named[k].grad.detach().clone() for k in keys}
+
+    both, g_both = run(sp_d, tp_d, slice(0, 2))
+    singles = [run(cut(sp_d, b), cut(tp_d, b), slice(b, b + 1)) for b in range(2)]
+    assert float(singles[0][0][0, 1]) != float(singles[1][0][0, 1])          # the subjects really differ
+    want = (singles[0][0] + singles[1][0]) / 2
+    assert torch.allclose(both, want, rtol=1e-5, atol=1e-8), (both, want)
+    # gradients: the same ill-conditioned sums as in tests/test_smooth_cpu.py (normalised gradients; this case has the
+    # density head at gain 300), and the order of the active points -- K1 compacts with atomics -- differs between the
+    # runs, so the comparison is the one used against the reference: largest-entry error and direction
+    for k in keys:
+        w = ((singles[0][1][k] + singles[1][1][k]) / 2).double().reshape(-1)
+        got = g_both[k].double().reshape(-1)
+        err = float((got - w).abs().max()) / max(float(w.abs().max()), 1e-30)
+        cos = float(got @ w) / max(float(got.norm() * w.norm()), 1e-300)
+        assert err <= 0.15 and cos >= 0.995, (k, err, cos)
