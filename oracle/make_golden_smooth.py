@@ -4,7 +4,8 @@ other_loss[0][0] computed by the UNMODIFIED reference's own autograd on CPU.  TE
 
     python oracle/make_golden_smooth.py
 
-Same scene / rays / weights as oracle/make_golden_train.py (tests/golden_cases.py TRAIN_CASE), global_step = 0 and
+Scene and rays of oracle/make_golden_train.py with a density head of moderate gain (tests/golden_cases.py SMOOTH_CASE:
+the terms are ill-conditioned where the occupancy saturates), global_step = 0 and
 smooth_interval = 4 (an interval step); the perturbation delta_x ~ N(0, 0.01) that the reference draws from the global
 RNG is drawn here from a seeded generator and stored, and handed to the reference through its module-level
 ``perturb_distri``.  Stores: delta_x, other_loss (4), the two normal fields of the unperturbed pass (columns 17:23 of
@@ -29,7 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from mpsnerf_b200 import synthetic  # noqa: E402
 from oracle import ref_shims  # noqa: E402
 from oracle import train_oracle as TO  # noqa: E402
-from golden_cases import build_train_case  # noqa: E402
+from golden_cases import build_smooth_case  # noqa: E402
 
 SMOOTH_KEYS = [k for k in TO.dense_keys() if not k.startswith(("feature_linear", "views_linear", "rgb_linear"))] + TO.TRUNK_KEYS
 
@@ -45,7 +46,7 @@ class _FixedDelta:
 
 def main():
     torch.set_num_threads(1)
-    scene, sd, ids, S, u, target, msk = build_train_case()
+    scene, sd, ids, S, u, target, msk = build_smooth_case()
     work = tempfile.mkdtemp(prefix="mpsnerf_ref_")
     ref_shims.install(work, scene.smpl)
     R = ref_shims.load_reference(n_samples=S)

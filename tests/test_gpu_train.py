@@ -130,11 +130,11 @@ def strict_fp32_convs():
     torch.backends.cudnn.allow_tf32 = old
 
 
-def _train_setup():
+def _train_setup(spec=None):
     from golden_cases import build_train_case
     from mpsnerf_b200 import run_nerf_batch as R, synthetic
     from mpsnerf_b200.parser_config import config_parser
-    scene, sd, ids, S, u, target, msk = build_train_case()
+    scene, sd, ids, S, u, target, msk = build_train_case(spec)
     net = _net(scene, sd).train()
     R.configure(config_parser().parse_args(["--smooth_loss", "0"]))
     handle = R.NetworkHandle(net)
@@ -199,8 +199,9 @@ def test_smooth_step_against_reference_double_backward(strict_fp32_convs):
     Tolerances: see tests/test_smooth_cpu.py (the terms are functions of normalised gradients)."""
     from test_smooth_cpu import GOLD, check_smooth_grads, smooth_keys
     from mpsnerf_b200.parser_config import config_parser
+    from golden_cases import SMOOTH_CASE
     g = np.load(GOLD)
-    R, net, handle, kw, target, msk = _train_setup()
+    R, net, handle, kw, target, msk = _train_setup(SMOOTH_CASE)
     R.configure(config_parser().parse_args(["--smooth_loss", "1"]))
     sp = dict(kw["sp_input"])
     sp["global_step"] = torch.zeros(1, dtype=torch.long)
@@ -256,7 +257,9 @@ def test_smooth_step_batch_of_two_equals_the_per_subject_steps(strict_fp32_convs
     from mpsnerf_b200 import run_nerf_batch as R, synthetic
     from mpsnerf_b200.lib import skinnning_batch as SB
     from mpsnerf_b200.parser_config import config_parser
-    scenes, sd, sp, tp, models, g = load_batch_case("batch2")
+    from golden_cases import SMOOTH_CASE
+    scenes, _, sp, tp, models, g = load_batch_case("batch2")
+    sd = synthetic.seeded_state_dict(scenes[0].seed, SMOOTH_CASE["alpha_gain"], SMOOTH_CASE["alpha_bias"])
     SB.set_default_smpl_models(models)
     torch.manual_seed(0)
     net = SB.SKinningBatch(human_sample=1, use_f2d=1, use_trans=1, smooth_loss=1, num_instances=25, mean_shape=0,
@@ -297,12 +300,17 @@ def test_smooth_step_batch_of_two_equals_the_per_subject_steps(strict_fp32_convs
     assert float(singles[0][0][0, 1]) != float(singles[1][0][0, 1])          # the subjects really differ
     want = (singles[0][0] + singles[1][0]) / 2
     assert torch.allclose(both, want, rtol=1e-5, atol=1e-8), (both, want)
-    # gradients: the same ill-conditioned sums as in tests/test_smooth_cpu.py (normalised gradients; this case has the
-    # density head at gain 300), and the order of the active points -- K1 compacts with atomics -- differs between the
-    # runs, so the comparison is the one used against the reference: largest-entry error and direction
+    # gradients: the same ill-conditioned sums as in tests/test_smooth_cpu.py (one fp32 ulp on x_c moves single entries
+    # by ~4 %), and the order of the active points -- K1 compacts with atomics -- differs between the runs, so this is a
+    # consistency check of the batching (a subject dropped, doubled or mis-averaged would be off by 50 - 100 %), with
+    # generous bounds on the largest-entry error and the direction; numerically-zero gradients (the MLP biases) skipped
+    scale = max(float((singles[0][1][k] + singles[1][1][k]).norm()) / 2 for k in keys)
     for k in keys:
         w = ((singles[0][1][k] + singles[1][1][k]) / 2).double().reshape(-1)
         got = g_both[k].double().reshape(-1)
+        if float(w.norm()) < 1e-6 * scale:
+            assert float(got.norm()) < 1e-5 * scale, k
+            continue
         err = float((got - w).abs().max()) / max(float(w.abs().max()), 1e-30)
         cos = float(got @ w) / max(float(got.norm() * w.norm()), 1e-300)
-        assert err <= 0.15 and cos >= 0.995, (k, err, cos)
+        assert err <= 0.3 and cos >= 0.97, (k, err, cos)

@@ -17,17 +17,26 @@ def smooth_keys():
 
 
 def check_smooth_grads(grads, g, rtol_norm, rtol_val, min_cos):
-    """Per live parameter of the smooth term: L2 norm, 512 strided entries and their direction vs the reference's."""
-    worst = 0.0
+    """Per live parameter of the smooth term: L2 norm, 512 strided entries and their direction vs the reference's.
+    The biases of the ReLU MLP (and the last feed-forward bias) have a mathematically ZERO gradient -- a normalised
+    gradient of a piecewise-linear network does not depend on them -- and come out as rounding noise (~1e-13 against
+    ~1e-3 for the weights) in the reference and here: for those only the smallness is checked."""
+    scale = max(float(g["norm/" + k]) for k in smooth_keys())
+    worst = worst_norm = 0.0
+    min_seen = 1.0
     for k in smooth_keys():
         got = np.asarray(grads[k].detach().cpu(), dtype=np.float64).reshape(-1)
         n_ref = float(g["norm/" + k])
+        if n_ref < 1e-6 * scale:
+            assert np.linalg.norm(got) < 1e-6 * scale, (k, np.linalg.norm(got), n_ref)
+            continue
         assert abs(np.linalg.norm(got) - n_ref) <= rtol_norm * n_ref, (k, np.linalg.norm(got), n_ref)
         sel, val = g["idx/" + k], g["val/" + k].astype(np.float64)
         err = np.abs(got[sel] - val).max() / max(np.abs(val).max(), 1e-30)
         cos = float(got[sel] @ val) / max(np.linalg.norm(got[sel]) * np.linalg.norm(val), 1e-300)
-        worst = max(worst, err)
+        worst, worst_norm, min_seen = max(worst, err), max(worst_norm, abs(np.linalg.norm(got) - n_ref) / n_ref), min(min_seen, cos)
         assert err <= rtol_val and cos >= min_cos, (k, err, cos)
+    print(f"smooth gradients vs reference: worst norm error {worst_norm:.2e}, worst entry error {worst:.2e}, min cosine {min_seen:.6f}")
     return worst
 
 
@@ -53,10 +62,10 @@ def _locate(pts, c):
 
 
 def test_smooth_terms_and_gradients_match_reference_double_backward():
-    from golden_cases import build_train_case
+    from golden_cases import build_smooth_case
     from mpsnerf_b200 import smooth
     g = np.load(GOLD)
-    scene, sd, ids, S, u, target, msk = build_train_case()
+    scene, sd, ids, S, u, target, msk = build_smooth_case()
     net = _cpu_net(scene, sd)
     sp, tp = O.squeeze_inputs(scene.sp_input, scene.tp_input)
     c = O.frame_constants(O.smpl_tensors(scene.smpl), sp, tp)
@@ -92,12 +101,13 @@ def test_smooth_terms_and_gradients_match_reference_double_backward():
     named = dict(net.named_parameters())
     keys = smooth_keys()
     grads = torch.autograd.grad(other[0, 0], [named[k] for k in keys])
-    # Tolerances.  The loss is a function of NORMALISED gradients g / (|g| + 1e-8): points whose raw gradient is tiny
-    # contribute derivatives of order 1 / |g|, so the parameter gradients are ill-conditioned in fp32.  Measured on
-    # this case: moving x_c by one fp32 ulp (relative 1.2e-7) changes the gradient norms by up to 0.7 % and single
-    # entries by up to 4.5 % of the largest entry; evaluating the frame constants with the reference's fp32 formulas
-    # instead of the float64 -> fp32 contract moves the two losses by 3e-5.  Against the reference this chain sits at
-    # 0.64 % (norms) / 8.5 % (worst single entry, one bias) -- inside that noise; direction (cosine over the sampled
-    # entries) is checked beside it.
+    # Tolerances.  The terms are functions of NORMALISED gradients g / (|g| + 1e-8) of a piecewise-linear (ReLU)
+    # network: g is piecewise constant in x_c, a point within rounding of a ReLU kink switches its whole contribution,
+    # and points with a small raw gradient contribute derivatives of order 1 / |g| -- the parameter gradients are
+    # ill-conditioned in fp32 whatever the weight scale.  Measured on this case (tests/golden_cases.py SMOOTH_CASE):
+    # moving x_c by ONE fp32 ulp (relative 1.2e-7) changes the gradient norms by up to 0.39 % and single entries by up
+    # to 4.1 % of the tensor's largest; against the reference this chain sits at 0.37 % / 3.4 %, cosine >= 0.9998 --
+    # inside that noise.  (At the bench weight scale, density head x300, the same figures are 0.7 % / 4.5 % and
+    # 0.64 % / 8.5 %.)  The bounds below leave ~4x room over the measured noise.
     worst = check_smooth_grads(dict(zip(keys, grads)), g, rtol_norm=2e-2, rtol_val=0.15, min_cos=0.995)
     print("worst sampled-entry error", worst)
