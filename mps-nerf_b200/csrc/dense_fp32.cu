@@ -310,6 +310,41 @@ linear_tcgen05_kernel(const float* __restrict__ X, int ldx, const float* __restr
   if (warp == 0) tmem_dealloc(tm, kCols);
 }
 
+// The 1- and 3-wide heads (alpha, rgb): a warp per row, lanes stride over K (128 contiguous bytes per load), exact fp32
+// FMAs, shuffle reduction.  On a 16 x 8 MMA tile these layers waste 7/8 of the tensor work and took as long as a
+// 256 x 256 layer (47 us per 32 768 rows); they are bound by reading X once (33 MB: a few microseconds).
+template <int ACT>
+__global__ void __launch_bounds__(256)
+linear_narrow_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int K, const float* __restrict__ b,
+                     const float* Res, int ldr, float* Y, int ldy, int64_t M, int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* x = X + row * ldx;
+  for (int k = lane; k < K; k += 32) {
+    const float v = x[k];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (n < N) acc[n] = fmaf(v, __ldg(W + (size_t)n * K + k), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      if (n >= N) break;
+      float v = acc[n] + (b ? b[n] : 0.f);
+      if (ACT == 1) v = fmaxf(v, 0.f);
+      if (ACT == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+      if (Res) v += Res[row * ldr + n];
+      Y[row * ldy + n] = v;
+    }
+  }
+}
+
 // MPSNERF_FP32_GEMM = tcgen05 (default: 3xTF32, kind::tf32 tcgen05 tiles) | mma (3xTF32, warp-level mma.sync) |
 // simt (plain fp32 FMAs on the CUDA cores)
 static int fp32_gemm_mode() {
@@ -322,7 +357,7 @@ template <int ACT>
 static int launch_linear(const float* X, int ldx, const float* W, int K, const float* b, const float* Res, int ldr,
                          float* Y, int ldy, int64_t M, int N, cudaStream_t st) {
   const int mode = fp32_gemm_mode();
-  if (mode == 2 && N >= 32) {      // (the 1- and 3-wide heads stay on the warp-level path)
+  if (mode == 2 && N >= 32) {      // (the 1- and 3-wide heads: linear_narrow_kernel below)
     if (N > 160) {                 // wide layers: 256 outputs per tile, the activation rows are staged half as often
       constexpr int kN = 256;
       const size_t smem = 2 * (size_t)g_stage_bytes<kN>();
@@ -348,6 +383,10 @@ static int launch_linear(const float* X, int ldx, const float* W, int K, const f
       dim3 grid((unsigned)((M + kGRows - 1) / kGRows), (unsigned)((N + kN - 1) / kN));
       linear_tcgen05_kernel<ACT, kN><<<grid, kGThreads, smem, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
     }
+    return 0;
+  }
+  if (mode == 2 && N <= 4) {
+    linear_narrow_kernel<ACT><<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(X, ldx, W, K, b, Res, ldr, Y, ldy, M, N);
     return 0;
   }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
