@@ -111,3 +111,79 @@ def test_smooth_terms_and_gradients_match_reference_double_backward():
     # 0.64 % / 8.5 %.)  The bounds below leave ~4x room over the measured noise.
     worst = check_smooth_grads(dict(zip(keys, grads)), g, rtol_norm=2e-2, rtol_val=0.15, min_cos=0.995)
     print("worst sampled-entry error", worst)
+
+
+# ------------------------------------------------------------------------------- building blocks of smooth.py
+def test_bilinear_read_equals_border_grid_sample_and_is_twice_differentiable():
+    """smooth.bilinear_read = the reference's gather-based read (lib/encoder.py:12-62): same values and first
+    derivatives as F.grid_sample(bilinear, border, align_corners=True), inside and outside the image -- and, unlike
+    grid_sample, a second derivative (gradgradcheck in float64)."""
+    import torch.nn.functional as F
+    from mpsnerf_b200 import smooth
+    g = torch.Generator().manual_seed(3)
+    V, C, IH, IW, n = 2, 5, 9, 11, 64
+    W, H = 22.0, 18.0                                  # image size in pixels (the latent is half resolution)
+    img = torch.randn(V, C, IH, IW, generator=g, dtype=torch.float64, requires_grad=True)
+    uv = (torch.rand(V, n, 2, generator=g, dtype=torch.float64) * 1.4 - 0.2) * torch.tensor([W, H], dtype=torch.float64)
+    uv.requires_grad_(True)
+    size = torch.tensor([W, H], dtype=torch.float64)
+    got = smooth.bilinear_read(img, uv, size)                                      # (V,n,C)
+    want = F.grid_sample(img, (2.0 * uv / size - 1.0)[:, :, None], mode="bilinear", padding_mode="border",
+                         align_corners=True)[..., 0].transpose(1, 2)
+    assert torch.allclose(got, want, atol=1e-12)
+    w = torch.randn(V, n, C, generator=g, dtype=torch.float64)
+    ga = torch.autograd.grad((got * w).sum(), [img, uv])
+    gb = torch.autograd.grad((want * w).sum(), [img, uv])
+    assert torch.allclose(ga[0], gb[0], atol=1e-12) and torch.allclose(ga[1], gb[1], atol=1e-10)
+    small_img = img[:, :2, :4, :4].detach().clone().requires_grad_(True)
+    small_uv = (torch.rand(2, 6, 2, generator=g, dtype=torch.float64) * 0.8 + 0.1) * size
+    small_uv.requires_grad_(True)
+    assert torch.autograd.gradgradcheck(lambda a, b: smooth.bilinear_read(a, b, size), (small_img, small_uv), atol=1e-6)
+
+
+def test_inverse3_and_canonical_to_pixels():
+    """smooth.inverse3 (adjugate) vs torch.linalg.inv; canonical_to_pixels vs the oracle's numpy stages
+    (canonical2source + projection) on the training case, and its double backward (gradgradcheck, float64)."""
+    from golden_cases import build_smooth_case
+    from mpsnerf_b200 import smooth
+    g = torch.Generator().manual_seed(4)
+    A = torch.randn(50, 3, 3, generator=g, dtype=torch.float64) + 2 * torch.eye(3, dtype=torch.float64)
+    assert torch.allclose(smooth.inverse3(A), torch.linalg.inv(A), atol=1e-10)
+    scene, sd, ids, S, u, target, msk = build_smooth_case()
+    sp, tp = O.squeeze_inputs(scene.sp_input, scene.tp_input)
+    c = O.frame_constants(O.smpl_tensors(scene.smpl), sp, tp)
+    fr = {"A_big_sp": torch.from_numpy(c["A_big_sp"]).reshape(24, 12), "A_sp": torch.from_numpy(c["A_sp"]).reshape(24, 12),
+          "Rinv_sp": torch.from_numpy(c["Rinv_sp"]), "Th_sp": torch.from_numpy(c["Th_sp"]),
+          "cam_R": sp["R_all"].float(), "cam_T": sp["T_all"].float().reshape(-1, 3), "cam_K": sp["K_all"].float()}
+    pts = O.sample_points(scene.rays_o[ids].astype(np.float32), scene.rays_d[ids].astype(np.float32),
+                          O.sample_z(scene.near[ids], scene.far[ids], S, u)).reshape(-1, 3)
+    act, xc, idx3 = _locate(pts, c)
+    idx3_o, xs, xw, w = O.canonical2source(xc.numpy(), c)
+    assert np.array_equal(idx3_o, idx3.numpy())
+    uv = smooth.canonical_to_pixels(xc, torch.from_numpy(w), fr)
+    want = O.projection(xw, sp["R_all"], sp["T_all"], sp["K_all"])
+    assert torch.allclose(uv, want.float(), atol=2e-3)          # pixels; two fp32 evaluation orders of the same chain
+    f64 = {k: v.double() for k, v in fr.items()}
+    x64 = xc[:5].double().requires_grad_(True)
+    assert torch.autograd.gradgradcheck(lambda x: smooth.canonical_to_pixels(x, torch.from_numpy(w[:5]).double(), f64), (x64,),
+                                        atol=1e-5)
+
+
+def test_vertex_normals_are_the_sequential_last_face_wins_definition():
+    """smooth.vertex_normals vs the reference's compute_normal statement by statement, executed sequentially (numpy
+    fancy-index `+=`: the last of the repeated indices wins): identical winners, unit length."""
+    from mpsnerf_b200 import smooth, synthetic
+    smpl = synthetic.make_smpl("n", 3)
+    v = np.asarray(smpl["v_template"], dtype=np.float32)
+    f = np.asarray(smpl["f"]).astype(np.int64)
+    got = smooth.vertex_normals(torch.from_numpy(v), torch.from_numpy(f)).numpy()
+    tri = torch.from_numpy(v)[torch.from_numpy(f)]
+    n = torch.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], dim=-1)
+    n = (n / torch.sqrt((n ** 2).sum(-1, keepdim=True)).clamp_min(1e-8)).numpy()
+    norm = np.zeros_like(v)
+    for s in range(3):
+        norm[f[:, s]] += n                               # numpy: sequential, no accumulation over repeated indices
+    norm /= np.maximum(np.sqrt((norm ** 2).sum(-1, keepdims=True)), 1e-8)
+    np.testing.assert_allclose(got, norm, atol=1e-6)
+    lens = np.sqrt((got ** 2).sum(-1))
+    assert np.all((np.abs(lens - 1) < 1e-5) | (lens == 0))
