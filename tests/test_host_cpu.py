@@ -218,3 +218,39 @@ def test_bench_reference_arm_prints_the_contract_line(monkeypatch, capsys):
     monkeypatch.setenv("WORLD_SIZE", "8")
     a = argparse.Namespace(gpus=8, steps=1, warmup=0, workload=None, mode="auto")
     assert bench.resolve_mode(a) == (8, "h36m", True)
+
+
+def test_header_is_plain_c_and_a_c_host_links_against_the_library(tmp_path):
+    """include/mpsnerf.h is the drop-in boundary: it must compile as C99 (no C++ in the signatures), and a C host that
+    binds the entry points the way INTEGRATION.md describes must link against the in-tree .so and reach the functions
+    that need no GPU (ABI version, argument validation with the thread-local error string, workspace sizes)."""
+    import subprocess
+    from mpsnerf_b200 import build
+    lib = build.build()
+    libdir, root = os.path.dirname(lib), os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "mpsnerf.h"
+int main(void) {
+  if (mpsnerf_abi_version() != MPSNERF_ABI_VERSION) return 1;
+  /* a call with a missing pointer is refused on the host, before any CUDA work, and says why */
+  if (mpsnerf_allreduce_mean(NULL, NULL, 4, NULL) != MPSNERF_EINVAL) return 2;
+  if (strstr(mpsnerf_last_error(), "mpsnerf_allreduce_mean") == NULL) return 3;
+  if (mpsnerf_allreduce_mean(NULL, NULL, 0, NULL) != MPSNERF_OK) return 4;      /* empty bucket: nothing to do */
+  if (mpsnerf_grid_bytes(6890) == 0) return 5;
+  if (mpsnerf_dense_train_workspace(1000, 3) == 0 || mpsnerf_render_rays_workspace(1024, 64, 3, 65536) == 0) return 6;
+  printf("abi %d frame %zu bytes\n", mpsnerf_abi_version(), sizeof(mpsnerf_frame));
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-lmpsnerf_b200", "-Wl,-rpath," + libdir])
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":/usr/local/cuda/lib64:" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([str(exe)], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    from mpsnerf_b200 import _lib
+    import ctypes
+    assert out.stdout.split() == ["abi", "1", "frame", str(ctypes.sizeof(_lib.Frame)), "bytes"]
