@@ -254,3 +254,36 @@ int main(void) {
     from mpsnerf_b200 import _lib
     import ctypes
     assert out.stdout.split() == ["abi", "1", "frame", str(ctypes.sizeof(_lib.Frame)), "bytes"]
+
+
+def test_create_nerf_resumes_from_the_last_checkpoint(tmp_path):
+    """create_nerf (ref run_nerf_batch.py:301-366): same five return values and render_kwargs keys; resumes from the
+    lexicographically last ``*.tar`` under basedir/expname in the reference's checkpoint format
+    ({'global_step', 'network_fn_state_dict'}, :606-617) unless --no_reload; --ft_path names one explicitly."""
+    from mpsnerf_b200 import run_nerf_batch as R, synthetic
+    from mpsnerf_b200.lib import skinnning_batch as SB
+    from mpsnerf_b200.parser_config import config_parser
+    SB.set_default_smpl_models(synthetic.make_smpl("n", 0))
+    exp = tmp_path / "exp"
+    exp.mkdir()
+    cfg = ["--config", os.path.join(ROOT, "configs", "canonical_transformer.txt"), "--basedir", str(tmp_path), "--expname", "exp"]
+    cpu = torch.device("cpu")
+    tr, te, start, grad_vars, opt = R.create_nerf(config_parser().parse_args(cfg), device=cpu)
+    assert start == 0
+    assert set(tr) == {"network_query_fn", "perturb", "N_samples", "network_fn", "use_viewdirs", "N_importance"}
+    assert set(te) == set(tr) and te["perturb"] is False and tr["perturb"] == 1.0 and tr["network_fn"] is te["network_fn"]
+    net = R._net_of(tr["network_fn"])
+    assert len(grad_vars) == len(list(net.parameters())) and isinstance(opt, torch.optim.Adam)
+    assert opt.param_groups[0]["lr"] == config_parser().parse_args(cfg).lrate
+    # two checkpoints: the later one wins; the earlier one can be named with --ft_path
+    sd_a = {k: v.clone() for k, v in net.state_dict().items()}
+    sd_b = {k: (v + 1.0 if v.is_floating_point() else v.clone()) for k, v in sd_a.items()}
+    torch.save({"global_step": 1000, "network_fn_state_dict": sd_a}, str(exp / "001000.tar"))
+    torch.save({"global_step": 2000, "network_fn_state_dict": sd_b}, str(exp / "002000.tar"))
+    key = "pts_linears.3.weight"
+    tr2, _, start2, _, _ = R.create_nerf(config_parser().parse_args(cfg), device=cpu)
+    assert start2 == 2000 and torch.equal(R._net_of(tr2["network_fn"]).state_dict()[key], sd_b[key])
+    tr3, _, start3, _, _ = R.create_nerf(config_parser().parse_args(cfg + ["--ft_path", "001000.tar"]), device=cpu)
+    assert start3 == 1000 and torch.equal(R._net_of(tr3["network_fn"]).state_dict()[key], sd_a[key])
+    _, _, start4, _, _ = R.create_nerf(config_parser().parse_args(cfg + ["--no_reload"]), device=cpu)
+    assert start4 == 0
