@@ -50,15 +50,44 @@ class DenseBucket:
         self.work = None            # handle of the in-flight all-reduce
         self.world = 1
         self.deferred = False       # smooth step: autograd also writes p.grad; the all-reduce waits for absorb_autograd()
+        # Two ways to drive a step.  EXPLICIT (TrainStep): begin_step() ... backward ... absorb_autograd() / finish(),
+        # with the all-reduce launched from inside the backward.  AUTOMATIC (the reference's own loop, unchanged:
+        # render -> loss.backward() -> optimizer.step(), run_nerf_batch.py:544-563): the first render node of a step
+        # opens it, and a callback queued on the autograd engine closes it when the backward pass has finished.
+        self.explicit = False
+        self.open = False
+        self.trunk = [p for k, p in named.items() if k.startswith("encoder_2d.")]
+        self._callback_queued = False
 
     def begin_step(self, world):
         self.flat.zero_()
         self.pending, self.work, self.world, self.deferred = 0, None, world, False
+        self.explicit, self.open = True, True
+
+    def node_forward(self):
+        """Called by every render node's forward.  Opens an automatic step if no step is open: the buffer is zeroed
+        unless the parameters' .grad still ARE its views (the caller did not zero them: torch's accumulate-into-.grad
+        semantics, then, also for the kernels' share)."""
+        if not self.open:
+            kept = self.params[0].grad is not None and self.params[0].grad.data_ptr() == self.views[0].data_ptr()
+            if not kept:
+                self.flat.zero_()
+            self.pending, self.work, self.deferred = 0, None, False
+            self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            self.explicit, self.open, self._callback_queued = False, True, False
+        self.pending += 1
+
+    def node_backward_begin(self):
+        """Called at the start of every render node's backward: in an automatic step, have the autograd engine call
+        auto_finalize() once this backward pass is complete (the hook DistributedDataParallel finalises with)."""
+        if not self.explicit and not self._callback_queued:
+            self._callback_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.auto_finalize)
 
     def node_done(self):
-        """Called at the end of every render node's backward; the last one launches the all-reduce."""
+        """Called at the end of every render node's backward; in an explicit step the last one launches the all-reduce."""
         self.pending -= 1
-        if self.pending == 0 and self.world > 1 and not self.deferred:
+        if self.explicit and self.pending == 0 and self.world > 1 and not self.deferred:
             self.work = dist.all_reduce(self.flat, async_op=True)
 
     def absorb_autograd(self):
@@ -80,6 +109,36 @@ class DenseBucket:
             self.flat.div_(self.world)
         for p, v in zip(self.params, self.views):
             p.grad = v
+        self.explicit, self.open = False, False
+
+    def auto_finalize(self):
+        """End of the backward pass of an automatic step: merge what autograd itself accumulated for the dense
+        parameters (smooth steps), average over the ranks (dense bucket and encoder-trunk gradients), and leave every
+        gradient in ``.grad`` -- ``optimizer.step()`` can follow, as in the reference's loop."""
+        self._callback_queued = False
+        if self.explicit or not self.open:
+            return
+        self.deferred = True
+        self.absorb_autograd()
+        if self.world > 1:
+            if self.work is None:
+                self.work = dist.all_reduce(self.flat, async_op=True)
+            allreduce_mean_(self.trunk, self.world)
+        self.finish()
+
+
+def allreduce_mean_(params, world):
+    """Average the gradients of ``params`` over the ranks in one flat all-reduce (the encoder trunk's, after cuDNN)."""
+    ps = [p for p in params if p.grad is not None]
+    if world <= 1 or not ps:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    o = 0
+    for p in ps:
+        p.grad.copy_(flat[o:o + p.numel()].view_as(p))
+        o += p.numel()
 
 
 class _RenderNode(torch.autograd.Function):
@@ -133,13 +192,14 @@ class _RenderNode(torch.autograd.Function):
         ctx.te, ctx.fctx, ctx.n, ctx.S, ctx.occupancy = te, fctx, n, S, occupancy
         ctx.keep = (rays8, t_vals, u, raw, act_pid, uv, ws, latent.shape)
         ctx.mark_non_differentiable(disp, raw, mask, sq, ss)
-        te.bucket.pending += 1
+        te.bucket.node_forward()
         return rgb, acc, disp, raw, mask, sq, ss
 
     @staticmethod
     def backward(ctx, d_rgb, d_acc, *_):
         te, fctx, n, S = ctx.te, ctx.fctx, ctx.n, ctx.S
         lib = te.eng.lib
+        te.bucket.node_backward_begin()
         rays8, t_vals, u, raw, act_pid, uv, ws, lshape = ctx.keep
         dev = raw.device
         N, V = rays8.shape[0], fctx.n_views
@@ -310,15 +370,4 @@ class TrainStep:
 
     def allreduce_trunk(self, world):
         """Average the encoder-trunk gradients over the ranks in one flat all-reduce."""
-        if world <= 1:
-            return
-        ps = [p for p in self.net.encoder_2d.parameters() if p.grad is not None]
-        if not ps:
-            return
-        flat = torch.cat([p.grad.reshape(-1) for p in ps])
-        dist.all_reduce(flat)
-        flat.div_(world)
-        o = 0
-        for p in ps:
-            p.grad.copy_(flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
+        allreduce_mean_(list(self.net.encoder_2d.parameters()), world)

@@ -171,6 +171,28 @@ def test_training_step_gradients_against_reference_autograd(strict_fp32_convs):
     assert not [k for k, p in named.items() if p.grad is not None and k not in live]
 
 
+def test_training_step_in_the_reference_loop_without_trainstep(strict_fp32_convs):
+    """The reference's loop body unchanged (run_nerf_batch.py:544-563): render -> loss -> loss.backward(), no
+    TrainStep and no bucket calls.  The gradient bucket opens its step at the first render node and closes it from a
+    callback on the autograd engine, so every live parameter has its .grad when backward() returns -- the same
+    gradients as the reference's autograd -- and a second step after zero_grad() reproduces them."""
+    from test_train_oracle import GOLD, check_grads_against_golden
+    from oracle import train_oracle as TO
+    g = np.load(GOLD)
+    R, net, handle, kw, target, msk = _train_setup()
+    named = dict(net.named_parameters())
+    opt = torch.optim.Adam(list(net.parameters()), lr=0.0)
+    for _ in range(2):
+        opt.zero_grad()
+        rgb, disp, acc, extras = R.render(network_fn=handle, **kw)
+        loss = torch.mean((rgb - target) ** 2) + torch.mean((msk.squeeze(2) - acc) ** 2)
+        loss.backward()
+        grads = {k: named[k].grad for k in TO.dense_keys() + TO.TRUNK_KEYS}
+        assert all(v is not None for v in grads.values())
+        check_grads_against_golden(grads, g, rtol_norm=2e-3, rtol_val=2e-2)
+        opt.step()
+
+
 def test_train_step_optimises():
     """TrainStep on one fixed batch: Adam steps through the CUDA path reduce the loss, parameters and BN statistics move."""
     from mpsnerf_b200.train import TrainStep
